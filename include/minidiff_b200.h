@@ -1,0 +1,168 @@
+/*
+ * minidiff_b200 -- C ABI of the B200-native array backend for minidiff.
+ *
+ * This is the drop-in boundary: plain pointers, sizes and POD descriptors, no torch / C++ types.
+ * The reference (ahoynodnarb/minidiff) has NO native layer; its boundary is the table of NumPy
+ * functions a backend plugin exports (minidiff/backend/numpy.py:14-206, copied into the
+ * `minidiff.backend` namespace by minidiff/backend/__init__.py:80-85) plus a handful of raw-array
+ * protocol methods (`.astype`, `+=` family, `__setitem__`; minidiff/tensor.py:105,269-379).
+ * Each entry point below names the reference interface it stands behind.  The Python shim that
+ * binds these with ctypes is minidiff_b200/backend/_lib.py; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; mdb_last_error() gives the text
+ *     (the Python shim raises ValueError for MDB_EINVAL-class errors, RuntimeError otherwise,
+ *     matching the exception types NumPy raises through the reference: SURVEY 8b "Errors").
+ *   - all work is enqueued on ONE compute stream owned by the library (mdb_stream()); calls
+ *     return immediately, only mdb_sync / mdb_d2h / mdb_item wait (reference semantics are
+ *     synchronous eager; only as_numpy/item/repr observe values: SURVEY 8b "Threading").
+ *   - strides are in ELEMENTS, may be 0 (broadcast view) or negative (flip view).
+ */
+#ifndef MINIDIFF_B200_H
+#define MINIDIFF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDB_MAX_DIMS 8
+#define MDB_ABI_VERSION 1
+
+/* status codes */
+enum { MDB_OK = 0, MDB_EINVAL = 1, MDB_ECUDA = 2, MDB_ENOMEM = 3, MDB_ENOTSUP = 4, MDB_ECOMM = 5 };
+
+/* element types (mirrors the dtype objects a backend exports: backend/numpy.py:188-200) */
+typedef enum {
+  MDB_BOOL = 0, MDB_U8 = 1, MDB_I8 = 2, MDB_I16 = 3, MDB_I32 = 4, MDB_I64 = 5,
+  MDB_F32 = 6, MDB_F64 = 7, MDB_U16 = 8, MDB_U32 = 9, MDB_U64 = 10, MDB_F16 = 11
+} mdb_dtype;
+
+/* strided view of device memory == what `backend.tensor_class` instances carry
+ * (shape/strides semantics of numpy.ndarray, the reference's tensor_class: backend/numpy.py:15-16) */
+typedef struct {
+  void*   ptr;                    /* address of element [0,...,0] (NULL for an immediate) */
+  int32_t dtype;                  /* mdb_dtype */
+  int32_t ndim;                   /* 0..MDB_MAX_DIMS */
+  int64_t shape[MDB_MAX_DIMS];
+  int64_t strides[MDB_MAX_DIMS];  /* elements */
+  double  imm;                    /* value when ptr == NULL: an un-promoted Python scalar operand
+                                     (reference passes them through unwrapped: wrapping.py:121-124) */
+  int64_t imm_i;                  /* integer image of imm (exact for int64 immediates) */
+} mdb_array;
+
+/* ---- elementwise op ids: one per backend function (backend/numpy.py:19-95) ------------------ */
+typedef enum {
+  /* unary */
+  MDB_OP_COPY = 0, MDB_OP_NEG, MDB_OP_ABS, MDB_OP_SIGN, MDB_OP_CEIL, MDB_OP_FLOOR,
+  MDB_OP_SIN, MDB_OP_COS, MDB_OP_TAN, MDB_OP_SINH, MDB_OP_COSH, MDB_OP_TANH,
+  MDB_OP_EXP, MDB_OP_LOG, MDB_OP_SQRT, MDB_OP_RECIP, MDB_OP_SQUARE, MDB_OP_LOGICAL_NOT,
+  MDB_OP_INVERT, MDB_OP_ISNAN,
+  /* binary */
+  MDB_OP_ADD = 32, MDB_OP_SUB, MDB_OP_MUL, MDB_OP_DIV, MDB_OP_POW, MDB_OP_MOD, MDB_OP_FLOORDIV,
+  MDB_OP_MAXIMUM, MDB_OP_MINIMUM,
+  MDB_OP_EQ, MDB_OP_NE, MDB_OP_GT, MDB_OP_GE, MDB_OP_LT, MDB_OP_LE,
+  MDB_OP_AND, MDB_OP_OR, MDB_OP_XOR,
+  /* ternary */
+  MDB_OP_WHERE = 64, MDB_OP_CLIP,
+  MDB_OP_FMA,        /* in0 + in1*in2, rounded as separate mul then add (== two backend calls) */
+  /* fused backward forms (replace the call chains of ops/definitions.py grad lambdas; each is
+     rounded step by step exactly like the unfused chain so results are bit-identical) */
+  MDB_OP_SIN_BWD = 96,   /* g * cos(x)            definitions.py:378  */
+  MDB_OP_COS_BWD,        /* g * (-sin(x))         definitions.py:313  */
+  MDB_OP_EXP_BWD,        /* g * exp(x)            definitions.py:321  */
+  MDB_OP_LOG_BWD,        /* g / x                 definitions.py:342  */
+  MDB_OP_TANH_BWD,       /* g * (1/cosh(x)**2)    definitions.py:414  */
+  MDB_OP_POW_BWD,        /* (g*p) * x**(p-1), p = immediate in2   definitions.py:509 */
+  MDB_OP_DIV_BWD_Y,      /* g * (-x / y**2)       definitions.py:531  */
+  MDB_OP_RELU_MASK_BWD,  /* g * (x > 0)           where-grad_y definitions.py:557 with greater */
+} mdb_op;
+
+/* reductions (backend sum/mean/max/min/prod/any/all/argmax/argmin: backend/numpy.py:20-57) */
+typedef enum {
+  MDB_RED_SUM = 0, MDB_RED_MEAN, MDB_RED_MAX, MDB_RED_MIN, MDB_RED_PROD, MDB_RED_ANY, MDB_RED_ALL,
+  MDB_RED_ARGMAX, MDB_RED_ARGMIN
+} mdb_red;
+
+/* ---- runtime ------------------------------------------------------------------------------- */
+int         mdb_abi_version(void);
+const char* mdb_last_error(void);
+int         mdb_device_count(int* count);
+int         mdb_init(int device);                 /* idempotent; creates the compute stream      */
+int         mdb_shutdown(void);
+int         mdb_device_info(int* sm_count, size_t* total_bytes, int* cc_major, int* cc_minor);
+void*       mdb_stream(void);                     /* cudaStream_t of the compute stream          */
+int         mdb_sync(void);
+
+/* caching allocator (size-class free lists; stream-ordered reuse on the compute stream).
+ * Stands behind every array a backend function returns + DeviceArray finalizers (SURVEY 8b
+ * "Ownership"). */
+int mdb_alloc(size_t bytes, void** out);
+int mdb_free(void* ptr);
+int mdb_empty_cache(void);
+int mdb_mem_stats(size_t* in_use, size_t* cached, size_t* peak_in_use, uint64_t* n_device_allocs);
+int mdb_host_alloc(size_t bytes, void** out);     /* pinned host memory for H2D/D2H staging      */
+int mdb_host_free(void* ptr);
+
+/* tensor_constructor / as_numpy / tensor_item (backend/numpy.py:15,161-163,204-206) */
+int mdb_h2d(void* dst, const void* src, size_t bytes);         /* async if src is pinned          */
+int mdb_d2h(void* dst, const void* src, size_t bytes);         /* waits for completion            */
+int mdb_d2d(void* dst, const void* src, size_t bytes);
+
+/* timing on the compute stream (bench.py: CUDA events on the launching stream) */
+int mdb_event_create(void** ev);
+int mdb_event_record(void* ev);
+int mdb_event_elapsed_ms(void* start, void* stop, float* ms);  /* syncs on `stop`                 */
+int mdb_event_destroy(void* ev);
+uint64_t mdb_launch_count(void);                  /* kernels launched by this library so far     */
+
+/* ---- compute ------------------------------------------------------------------------------- */
+/* ones_like/zeros_like/full/full_like (backend/numpy.py:98-103) */
+int mdb_fill(const mdb_array* out, double value);
+/* copy / astype / ascontiguous / broadcast materialisation / `a[key] = v` on basic keys
+ * (backend/numpy.py:29,63-65; tensor.py:376-379): out[...] = cast(in[...]) with broadcasting */
+int mdb_copy(const mdb_array* out, const mdb_array* in);
+/* every elementwise backend function; `out` may alias in[0] exactly (the `+=` family of
+ * tensor.py:269-362).  Inputs broadcast against out's shape (stride 0 where stretched). */
+int mdb_elementwise(int op, const mdb_array* out, int n_in, const mdb_array* in);
+/* sum/mean/max/min/prod/any/all/argmax/argmin over the axes whose bit is set in axis_mask;
+ * `out` is given in keepdims form (same ndim as `in`, reduced extents 1). */
+int mdb_reduce(int red, const mdb_array* out, const mdb_array* in, uint32_t axis_mask);
+/* fused "un-broadcast": out (+)= sum over the stretched axes of op(in...) where out's extents
+ * are 1 on the reduced axes (replaces grad-lambda -> md.unbroadcast -> `grad + new` of
+ * topology.py:93-104 + definitions.py:157-183 with one pass). accumulate: 0 store, 1 add. */
+int mdb_elementwise_reduce(int op, const mdb_array* out, int n_in, const mdb_array* in,
+                           int accumulate);
+/* matmul (backend/numpy.py:84) for 2-D operands of any row/column-major mix, fp32, 3xTF32 on
+ * tcgen05 tensor cores when shapes allow, else an fp32 CUDA-core kernel.
+ * C = A@B (accumulate=0) or C += A@B (accumulate=1, the in-place form of topology.py:101-104). */
+int mdb_gemm(const mdb_array* c, const mdb_array* a, const mdb_array* b, int accumulate);
+int mdb_gemm_config(int force_path);              /* 0 auto, 1 SIMT only, 2 tcgen05 only (tests)  */
+
+/* integer-array indexing (getitem / `a[key] = v` / index_add with array keys:
+ * backend/numpy.py:73-75,105; tensor.py:376-379) over the leading axis:
+ *   gather : out[i, ...] = src[idx[i], ...]
+ *   scatter: dst[idx[i], ...] = src[i, ...]  (add=0)   or   += (add=1, duplicates accumulate,
+ *            the np.add.at semantics getitem_grad relies on: ops/definitions.py:186-189)
+ * idx is a contiguous int64 vector; negative entries wrap.  src of scatter may broadcast
+ * (stride 0). */
+int mdb_gather_rows(const mdb_array* out, const mdb_array* src, const mdb_array* idx);
+int mdb_scatter_rows(const mdb_array* dst, const mdb_array* src, const mdb_array* idx, int add);
+
+/* counter-based RNG on device (rand / randn: backend/numpy.py:131-134) */
+int mdb_random(const mdb_array* out, int normal, uint64_t seed, uint64_t offset);
+
+/* ---- data-parallel exchange (config 4; no counterpart in the reference: SURVEY 2.1) --------- */
+int mdb_comm_unique_id(void* id128, const char* nccl_lib_path);          /* rank 0               */
+int mdb_comm_init(int rank, int world, const void* id128, const char* nccl_lib_path);
+int mdb_comm_allreduce_f32(void* ptr, size_t count, int average);        /* on the comm stream,
+                                                                            ordered after compute */
+int mdb_comm_wait(void);                          /* compute stream waits for the comm stream    */
+int mdb_comm_destroy(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MINIDIFF_B200_H */

@@ -1,0 +1,38 @@
+"""`minidiff_b200.backend`: the single (B200) array backend.
+
+Mirrors the *namespace* the reference builds in `minidiff.backend` after its loader has copied a
+plugin class's attributes into module globals (reference backend/__init__.py:80-85): the same 114
+names, here bound directly to the device implementation -- there is one CUDA
+path, no backend search order, no silent NumPy fallback (reference backend/__init__.py:37-59 falls
+back silently; this module raises at import if the shared library is missing).
+"""
+from . import _lib  # noqa: F401  (raises ImportError if libminidiff_b200.so is absent)
+from . import functions as _F
+from .device_array import DeviceArray
+
+globals().update(_F.TABLE)
+BACKEND_NAME = "minidiff_b200 (sm_100a CUDA, C ABI v%d)" % _lib.lib.mdb_abi_version()
+
+# extras beyond the reference table (used by the engine's fused paths, tests and bench)
+synchronize = _F.synchronize
+seed = _F.seed
+asarray = _F.asarray
+negative = _F.negative
+elementwise_into = _F.elementwise_into
+copy_into = _F.copy_into
+
+
+class Backend:
+    """Base class marker, kept for symmetry with the reference's plugin protocol
+    (reference backend/__init__.py:755-759)."""
+
+    def __init__(self):
+        raise NotImplementedError("Backend classes are namespaces, not instantiable")
+
+
+def assert_live() -> None:
+    """The reference's loader swallows plugin import errors (SURVEY finding 6); callers that need
+    certainty that arithmetic runs on the GPU call this."""
+    if globals()["tensor_class"] is not DeviceArray:
+        raise RuntimeError("minidiff_b200 backend is not the active backend")
+    _lib.ensure_device()

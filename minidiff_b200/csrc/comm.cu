@@ -1,0 +1,116 @@
+// Data-parallel gradient exchange for the MLP training step (BASELINE config 4).  The reference
+// has no distributed code at all; this is new: one process per GPU, NCCL over
+// NVLink 5 / NVSwitch, all-reduce issued on a dedicated comm stream that is ordered after the
+// compute stream by an event so the exchange of late-layer gradients overlaps the remaining
+// backward GEMMs.  libnccl is dlopen()ed (path supplied by the host shim: the torch-bundled
+// libnccl.so.2) so the library itself loads on machines without NCCL.
+#include <dlfcn.h>
+#include <string.h>
+
+#include "mdb_common.cuh"
+
+namespace mdb {
+
+struct NcclUniqueId { char internal[128]; };
+typedef void* ncclComm_t;
+typedef int (*fn_GetUniqueId)(NcclUniqueId*);
+typedef int (*fn_CommInitRank)(ncclComm_t*, int, NcclUniqueId, int);
+typedef int (*fn_AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
+typedef int (*fn_CommDestroy)(ncclComm_t);
+typedef const char* (*fn_GetErrorString)(int);
+
+static void* g_nccl = nullptr;
+static fn_GetUniqueId p_GetUniqueId;
+static fn_CommInitRank p_CommInitRank;
+static fn_AllReduce p_AllReduce;
+static fn_CommDestroy p_CommDestroy;
+static fn_GetErrorString p_GetErrorString;
+static ncclComm_t g_comm = nullptr;
+static cudaStream_t g_comm_stream = nullptr;
+static cudaEvent_t g_ev_compute = nullptr, g_ev_comm = nullptr;
+static int g_world = 1;
+
+static int load_nccl(const char* path) {
+  if (g_nccl) return 0;
+  const char* cands[] = {path, "libnccl.so.2", "libnccl.so"};
+  for (const char* c : cands) {
+    if (!c || !*c) continue;
+    g_nccl = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl) break;
+  }
+  if (!g_nccl) return set_error(MDB_ECOMM, "cannot dlopen libnccl (%s)", dlerror());
+  p_GetUniqueId = (fn_GetUniqueId)dlsym(g_nccl, "ncclGetUniqueId");
+  p_CommInitRank = (fn_CommInitRank)dlsym(g_nccl, "ncclCommInitRank");
+  p_AllReduce = (fn_AllReduce)dlsym(g_nccl, "ncclAllReduce");
+  p_CommDestroy = (fn_CommDestroy)dlsym(g_nccl, "ncclCommDestroy");
+  p_GetErrorString = (fn_GetErrorString)dlsym(g_nccl, "ncclGetErrorString");
+  if (!p_GetUniqueId || !p_CommInitRank || !p_AllReduce || !p_CommDestroy || !p_GetErrorString)
+    return set_error(MDB_ECOMM, "libnccl is missing required symbols");
+  return 0;
+}
+#define MDB_NCCL(call)                                                                          \
+  do {                                                                                          \
+    int r__ = (call);                                                                           \
+    if (r__ != 0) return set_error(MDB_ECOMM, "%s -> %s", #call, p_GetErrorString(r__));        \
+  } while (0)
+
+}  // namespace mdb
+
+using namespace mdb;
+
+extern "C" {
+
+int mdb_comm_unique_id(void* id128, const char* nccl_lib_path) {
+  MDB_TRY(load_nccl(nccl_lib_path));
+  NcclUniqueId id;
+  MDB_NCCL(p_GetUniqueId(&id));
+  memcpy(id128, &id, sizeof(id));
+  return 0;
+}
+
+int mdb_comm_init(int rank, int world, const void* id128, const char* nccl_lib_path) {
+  MDB_TRY(ensure_init());
+  MDB_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank %d / world %d", rank, world);
+  MDB_REQUIRE(g_comm == nullptr, "communicator already initialised");
+  MDB_TRY(load_nccl(nccl_lib_path));
+  NcclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  MDB_CUDA(cudaStreamCreateWithFlags(&g_comm_stream, cudaStreamNonBlocking));
+  MDB_CUDA(cudaEventCreateWithFlags(&g_ev_compute, cudaEventDisableTiming));
+  MDB_CUDA(cudaEventCreateWithFlags(&g_ev_comm, cudaEventDisableTiming));
+  MDB_NCCL(p_CommInitRank(&g_comm, world, id, rank));
+  g_world = world;
+  return 0;
+}
+
+int mdb_comm_allreduce_f32(void* ptr, size_t count, int average) {
+  MDB_REQUIRE(g_comm != nullptr, "communicator not initialised");
+  // comm stream waits for everything enqueued on the compute stream so far (the producer of ptr)
+  MDB_CUDA(cudaEventRecord(g_ev_compute, g_stream));
+  MDB_CUDA(cudaStreamWaitEvent(g_comm_stream, g_ev_compute, 0));
+  const int ncclFloat32 = 7, ncclSum = 0, ncclAvg = 4;
+  MDB_NCCL(p_AllReduce(ptr, ptr, count, ncclFloat32, average ? ncclAvg : ncclSum, g_comm,
+                       g_comm_stream));
+  MDB_CUDA(cudaEventRecord(g_ev_comm, g_comm_stream));
+  return 0;
+}
+
+int mdb_comm_wait(void) {
+  if (g_comm == nullptr) return 0;
+  MDB_CUDA(cudaStreamWaitEvent(g_stream, g_ev_comm, 0));
+  return 0;
+}
+
+int mdb_comm_destroy(void) {
+  if (g_comm) {
+    cudaStreamSynchronize(g_comm_stream);
+    p_CommDestroy(g_comm);
+    cudaStreamDestroy(g_comm_stream);
+    cudaEventDestroy(g_ev_compute);
+    cudaEventDestroy(g_ev_comm);
+    g_comm = nullptr;
+  }
+  return 0;
+}
+
+}  // extern "C"

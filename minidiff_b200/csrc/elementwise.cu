@@ -1,0 +1,383 @@
+// Elementwise backend functions (backend/numpy.py:19-95 + the in-place dunders of
+// tensor.py:269-362) as two kernels:
+//   ew_fast    : fp32 compute, <=3 collapsed dims, unit/zero inner strides -> 128-bit vectorised,
+//                4 independent loads in flight per thread, grid sized in multiples of the SM count
+//   ew_generic : any dtype / any strides (<=8 dims), one element per thread-iteration
+#include <limits>
+
+#include "ew_ops.cuh"
+
+namespace mdb {
+
+// ------------------------------------------------------------------------------------------------
+// host-side shape analysis
+// ------------------------------------------------------------------------------------------------
+int collapse(const mdb_array* out, int n_in, const mdb_array* in, Collapsed* c) {
+  const int nd = out->ndim;
+  MDB_REQUIRE(nd >= 0 && nd <= MDB_MAX_DIMS, "ndim %d out of range", nd);
+  int64_t shape[MDB_MAX_DIMS], ostr[MDB_MAX_DIMS], istr[3][MDB_MAX_DIMS];
+  for (int d = 0; d < nd; ++d) {
+    shape[d] = out->shape[d];
+    ostr[d] = out->strides[d];
+  }
+  for (int k = 0; k < n_in; ++k) {
+    const mdb_array& a = in[k];
+    if (a.ptr == nullptr) {  // immediate
+      for (int d = 0; d < nd; ++d) istr[k][d] = 0;
+      continue;
+    }
+    MDB_REQUIRE(a.ndim <= nd, "operands could not be broadcast together: input %d has %d dims, "
+                "output has %d", k, a.ndim, nd);
+    int lead = nd - a.ndim;
+    for (int d = 0; d < nd; ++d) {
+      if (d < lead) { istr[k][d] = 0; continue; }
+      int64_t ext = a.shape[d - lead];
+      if (ext == shape[d]) istr[k][d] = (ext == 1) ? 0 : a.strides[d - lead];
+      else if (ext == 1) istr[k][d] = 0;
+      else
+        return set_error(MDB_EINVAL, "operands could not be broadcast together: input %d extent "
+                         "%lld vs output extent %lld on axis %d", k, (long long)ext,
+                         (long long)shape[d], d);
+    }
+  }
+  // drop extent-1 axes, then merge (outer, inner) pairs every operand walks as one run
+  int m = 0;
+  for (int d = 0; d < nd; ++d) {
+    if (shape[d] == 1) continue;
+    if (m > 0) {
+      bool merge = c->ostr[m - 1] == ostr[d] * shape[d];
+      for (int k = 0; merge && k < n_in; ++k) merge = c->istr[k][m - 1] == istr[k][d] * shape[d];
+      if (merge) {
+        c->shape[m - 1] *= shape[d];
+        c->ostr[m - 1] = ostr[d];
+        for (int k = 0; k < n_in; ++k) c->istr[k][m - 1] = istr[k][d];
+        continue;
+      }
+    }
+    c->shape[m] = shape[d];
+    c->ostr[m] = ostr[d];
+    for (int k = 0; k < n_in; ++k) c->istr[k][m] = istr[k][d];
+    ++m;
+  }
+  if (m == 0) {
+    c->shape[0] = 1;
+    c->ostr[0] = 1;
+    for (int k = 0; k < n_in; ++k) c->istr[k][0] = 0;
+    m = 1;
+  }
+  c->ndim = m;
+  return 0;
+}
+
+static bool is_small_int(int dt) {
+  return dt == MDB_BOOL || dt == MDB_U8 || dt == MDB_I8 || dt == MDB_I16 || dt == MDB_U16;
+}
+
+// Which arithmetic the kernel computes in.  The result dtype (NumPy promotion, NEP 50 weak Python
+// scalars) is decided by the caller and arrives as out->dtype; predicates compare in the promoted
+// type of their inputs.
+int compute_class(int op, const mdb_array* out, int n_in, const mdb_array* in) {
+  if (!op_is_predicate(op) && out->dtype != MDB_BOOL) {
+    if (out->dtype == MDB_F32) return CC_F32;
+    if (out->dtype == MDB_F64) return CC_F64;
+    if (!op_float_only(op)) return CC_I64;
+    return CC_F64;
+  }
+  bool f64 = false, f32 = false, wide_int = false, imm_float = false, any_array = false;
+  for (int k = 0; k < n_in; ++k) {
+    if (in[k].ptr == nullptr) {
+      if (in[k].imm != (double)in[k].imm_i) imm_float = true;
+      if (in[k].dtype == MDB_F64 || in[k].dtype == MDB_F32) imm_float = true;
+      continue;
+    }
+    any_array = true;
+    int dt = in[k].dtype;
+    if (dt == MDB_F64) f64 = true;
+    else if (dt == MDB_F32) f32 = true;
+    else if (!is_small_int(dt)) wide_int = true;
+  }
+  if (f64 || (f32 && wide_int)) return CC_F64;
+  if (f32) return CC_F32;
+  if (imm_float || !any_array) return CC_F64;
+  return CC_I64;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fast kernel
+// ------------------------------------------------------------------------------------------------
+struct FastParams {
+  void* out;
+  int64_t os2, os1;
+  FastOperand in[3];
+  float aux;
+  uint32_t total;  // work items = rows * (inner / VEC)
+  FastDiv div_lv, div_d1;
+};
+
+template <int OP, int NIN, int VEC>
+__global__ void __launch_bounds__(256) ew_fast(const FastParams p) {
+  constexpr int U = 4;  // independent work items in flight per thread
+  constexpr bool PRED = op_is_predicate(OP);
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t base = blockIdx.x * blockDim.x + threadIdx.x; base < p.total; base += stride * U) {
+    float v[U][3][VEC];
+    int64_t ooff[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      uint32_t w = base + u * stride;
+      if (w < p.total) {
+        uint32_t row, cv, i2, i1;
+        p.div_lv.divmod(w, row, cv);
+        p.div_d1.divmod(row, i2, i1);
+        uint32_t col = cv * VEC;
+        ooff[u] = (int64_t)i2 * p.os2 + (int64_t)i1 * p.os1 + col;
+#pragma unroll
+        for (int k = 0; k < NIN; ++k) fast_load<VEC>(p.in[k], i2, i1, col, v[u][k]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      uint32_t w = base + u * stride;
+      if (w < p.total) {
+        float r[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+          r[j] = apply<OP, float>(v[u][0][j], NIN > 1 ? v[u][1][j] : 0.f,
+                                  NIN > 2 ? v[u][2][j] : 0.f, p.aux);
+        if constexpr (PRED) {
+          unsigned char* o = (unsigned char*)p.out + ooff[u];
+          if constexpr (VEC == 4)
+            *(uchar4*)o = make_uchar4(r[0] != 0.f, r[1] != 0.f, r[2] != 0.f, r[3] != 0.f);
+          else
+            *o = (unsigned char)(r[0] != 0.f);
+        } else {
+          float* o = (float*)p.out + ooff[u];
+          if constexpr (VEC == 4) *(float4*)o = make_float4(r[0], r[1], r[2], r[3]);
+          else *o = r[0];
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic kernel
+// ------------------------------------------------------------------------------------------------
+struct GenOperand {
+  const void* ptr;
+  int dtype;
+  int64_t str[MDB_MAX_DIMS];
+  double imm;
+  int64_t imm_i;
+};
+struct GenParams {
+  void* out;
+  int out_dtype, ndim;
+  int64_t shape[MDB_MAX_DIMS], ostr[MDB_MAX_DIMS];
+  int64_t total;
+  double aux;
+  GenOperand in[3];
+};
+
+template <typename T> __device__ __forceinline__ T imm_as(const GenOperand& o) {
+  if constexpr (std::is_integral_v<T>) return (T)o.imm_i; else return (T)o.imm;
+}
+
+template <int OP, int NIN, typename T>
+__global__ void __launch_bounds__(256) ew_generic(const GenParams p) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.total; i += stride) {
+    int64_t rem = i, oo = 0, off[3] = {0, 0, 0};
+    for (int d = p.ndim - 1; d >= 0; --d) {
+      int64_t q = rem / p.shape[d];
+      int64_t idx = rem - q * p.shape[d];
+      rem = q;
+      oo += idx * p.ostr[d];
+#pragma unroll
+      for (int k = 0; k < NIN; ++k) off[k] += idx * p.in[k].str[d];
+    }
+    T v[3] = {T(0), T(0), T(0)};
+#pragma unroll
+    for (int k = 0; k < NIN; ++k)
+      v[k] = p.in[k].ptr ? load_as<T>(p.in[k].ptr, p.in[k].dtype, off[k]) : imm_as<T>(p.in[k]);
+    T r = apply<OP, T>(v[0], v[1], v[2], (T)p.aux);
+    store_as<T>(p.out, p.out_dtype, oo, r);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dispatch
+// ------------------------------------------------------------------------------------------------
+#define MDB_UNARY_OPS(X)                                                                        \
+  X(MDB_OP_COPY) X(MDB_OP_NEG) X(MDB_OP_ABS) X(MDB_OP_SIGN) X(MDB_OP_CEIL) X(MDB_OP_FLOOR)      \
+  X(MDB_OP_SIN) X(MDB_OP_COS) X(MDB_OP_TAN) X(MDB_OP_SINH) X(MDB_OP_COSH) X(MDB_OP_TANH)        \
+  X(MDB_OP_EXP) X(MDB_OP_LOG) X(MDB_OP_SQRT) X(MDB_OP_RECIP) X(MDB_OP_SQUARE)                   \
+  X(MDB_OP_LOGICAL_NOT) X(MDB_OP_INVERT) X(MDB_OP_ISNAN)
+#define MDB_BINARY_OPS(X)                                                                       \
+  X(MDB_OP_ADD) X(MDB_OP_SUB) X(MDB_OP_MUL) X(MDB_OP_DIV) X(MDB_OP_POW) X(MDB_OP_MOD)           \
+  X(MDB_OP_FLOORDIV) X(MDB_OP_MAXIMUM) X(MDB_OP_MINIMUM) X(MDB_OP_EQ) X(MDB_OP_NE) X(MDB_OP_GT) \
+  X(MDB_OP_GE) X(MDB_OP_LT) X(MDB_OP_LE) X(MDB_OP_AND) X(MDB_OP_OR) X(MDB_OP_XOR)               \
+  X(MDB_OP_SIN_BWD) X(MDB_OP_COS_BWD) X(MDB_OP_EXP_BWD) X(MDB_OP_LOG_BWD) X(MDB_OP_TANH_BWD)    \
+  X(MDB_OP_RELU_MASK_BWD)
+#define MDB_TERNARY_OPS(X)                                                                      \
+  X(MDB_OP_WHERE) X(MDB_OP_CLIP) X(MDB_OP_FMA) X(MDB_OP_POW_BWD) X(MDB_OP_DIV_BWD_Y)
+
+template <int OP, int NIN>
+static int launch_fast(const FastParams& p, int vec, int grid) {
+  if (vec == 4) ew_fast<OP, NIN, 4><<<grid, 256, 0, g_stream>>>(p);
+  else ew_fast<OP, NIN, 1><<<grid, 256, 0, g_stream>>>(p);
+  MDB_CHECK_LAUNCH();
+  return 0;
+}
+
+template <int OP, int NIN>
+static int launch_generic(const GenParams& p, int cc, int grid) {
+  if (cc == CC_F32) ew_generic<OP, NIN, float><<<grid, 256, 0, g_stream>>>(p);
+  else if (cc == CC_F64) ew_generic<OP, NIN, double><<<grid, 256, 0, g_stream>>>(p);
+  else {
+    if constexpr (op_float_only(OP))
+      return set_error(MDB_ENOTSUP, "op %d is not defined for integer compute", OP);
+    else
+      ew_generic<OP, NIN, long long><<<grid, 256, 0, g_stream>>>(p);
+  }
+  MDB_CHECK_LAUNCH();
+  return 0;
+}
+
+static bool aligned(const void* p, size_t a) { return ((uintptr_t)p % a) == 0; }
+
+int elementwise_impl(int op, const mdb_array* out, int n_in, const mdb_array* in_user) {
+  MDB_TRY(ensure_init());
+  MDB_REQUIRE(out && out->ptr, "elementwise: output must be a device array");
+  mdb_array in[3];
+  for (int k = 0; k < n_in; ++k) in[k] = in_user[k];
+
+  // NumPy's exact scalar-exponent forms of power (SURVEY finding 5): rewrite to cheaper ops
+  if (op == MDB_OP_POW && in[1].ptr == nullptr && out->dtype != MDB_BOOL &&
+      (out->dtype == MDB_F32 || out->dtype == MDB_F64)) {
+    double e = in[1].imm;
+    if (e == 2.0) { op = MDB_OP_SQUARE; n_in = 1; }
+    else if (e == 1.0) { op = MDB_OP_COPY; n_in = 1; }
+    else if (e == 0.5) { op = MDB_OP_SQRT; n_in = 1; }
+    else if (e == -1.0) { op = MDB_OP_RECIP; n_in = 1; }
+    else if (e == 0.0) {
+      op = MDB_OP_COPY; n_in = 1;
+      in[0].ptr = nullptr; in[0].imm = 1.0; in[0].imm_i = 1; in[0].ndim = 0; in[0].dtype = MDB_F64;
+    }
+  }
+  MDB_REQUIRE(n_in == op_arity(op), "op %d takes %d inputs, got %d", op, op_arity(op), n_in);
+  double aux = 0.0;
+  if (op == MDB_OP_POW_BWD) {
+    MDB_REQUIRE(in[2].ptr == nullptr, "POW_BWD needs an immediate exponent");
+    aux = in[2].imm - 1.0;
+  }
+
+  Collapsed c;
+  MDB_TRY(collapse(out, n_in, in, &c));
+  int64_t total = 1;
+  for (int d = 0; d < c.ndim; ++d) total *= c.shape[d];
+  if (total == 0) return 0;
+  const int cc = compute_class(op, out, n_in, in);
+
+  // ---- fast path eligibility
+  const bool pred = op_is_predicate(op);
+  bool fast = cc == CC_F32 && c.ndim <= 3 && c.ostr[c.ndim - 1] == 1 &&
+              ((pred && (out->dtype == MDB_BOOL || out->dtype == MDB_U8)) ||
+               (!pred && out->dtype == MDB_F32));
+  for (int k = 0; fast && k < n_in; ++k) {
+    if (in[k].ptr == nullptr) continue;
+    int dt = in[k].dtype;
+    int64_t s0 = c.istr[k][c.ndim - 1];
+    fast = (dt == MDB_F32 || dt == MDB_BOOL || dt == MDB_U8) && (s0 == 0 || s0 == 1);
+  }
+  if (fast) {
+    const int nd = c.ndim;
+    int64_t L = c.shape[nd - 1];
+    int64_t d1 = nd >= 2 ? c.shape[nd - 2] : 1, d2 = nd >= 3 ? c.shape[nd - 3] : 1;
+    int64_t os1 = nd >= 2 ? c.ostr[nd - 2] : 0, os2 = nd >= 3 ? c.ostr[nd - 3] : 0;
+    const size_t osz = pred ? 1 : 4;
+    bool v4 = (L % 4 == 0) && aligned(out->ptr, 4 * osz) && os1 % 4 == 0 && os2 % 4 == 0;
+    FastParams p;
+    p.out = out->ptr; p.os1 = os1; p.os2 = os2; p.aux = (float)aux;
+    for (int k = 0; k < n_in; ++k) {
+      FastOperand& o = p.in[k];
+      o.ptr = in[k].ptr;
+      o.imm = (float)in[k].imm;
+      o.kind = in[k].ptr == nullptr ? K_IMM : (in[k].dtype == MDB_F32 ? K_F32 : K_U8);
+      o.s0 = (int)c.istr[k][nd - 1];
+      o.s1 = nd >= 2 ? c.istr[k][nd - 2] : 0;
+      o.s2 = nd >= 3 ? c.istr[k][nd - 3] : 0;
+      if (o.kind != K_IMM && o.s0 == 1) {
+        size_t esz = o.kind == K_F32 ? 4 : 1;
+        v4 = v4 && aligned(o.ptr, 4 * esz) && o.s1 % 4 == 0 && o.s2 % 4 == 0;
+      }
+    }
+    const int vec = v4 ? 4 : 1;
+    int64_t items = d2 * d1 * (L / vec);
+    if (items < (int64_t(1) << 31) && d2 * d1 < (int64_t(1) << 31)) {
+      p.total = (uint32_t)items;
+      p.div_lv = FastDiv((uint32_t)(L / vec));
+      p.div_d1 = FastDiv((uint32_t)d1);
+      int grid = grid_for((items + 3) / 4, 256);
+      switch (op) {
+#define X(OPID) case OPID: return launch_fast<OPID, 1>(p, vec, grid);
+        MDB_UNARY_OPS(X)
+#undef X
+#define X(OPID) case OPID: return launch_fast<OPID, 2>(p, vec, grid);
+        MDB_BINARY_OPS(X)
+#undef X
+#define X(OPID) case OPID: return launch_fast<OPID, 3>(p, vec, grid);
+        MDB_TERNARY_OPS(X)
+#undef X
+        default: return set_error(MDB_EINVAL, "unknown elementwise op %d", op);
+      }
+    }
+  }
+
+  // ---- generic path
+  GenParams g;
+  g.out = out->ptr; g.out_dtype = out->dtype; g.ndim = c.ndim; g.total = total; g.aux = aux;
+  for (int d = 0; d < c.ndim; ++d) { g.shape[d] = c.shape[d]; g.ostr[d] = c.ostr[d]; }
+  for (int k = 0; k < n_in; ++k) {
+    g.in[k].ptr = in[k].ptr; g.in[k].dtype = in[k].dtype;
+    g.in[k].imm = in[k].imm; g.in[k].imm_i = in[k].imm_i;
+    for (int d = 0; d < c.ndim; ++d) g.in[k].str[d] = c.istr[k][d];
+    MDB_REQUIRE(in[k].ptr == nullptr || in[k].dtype != MDB_F16, "float16 is not supported");
+  }
+  MDB_REQUIRE(out->dtype != MDB_F16, "float16 is not supported");
+  int grid = grid_for(total, 256);
+  switch (op) {
+#define X(OPID) case OPID: return launch_generic<OPID, 1>(g, cc, grid);
+    MDB_UNARY_OPS(X)
+#undef X
+#define X(OPID) case OPID: return launch_generic<OPID, 2>(g, cc, grid);
+    MDB_BINARY_OPS(X)
+#undef X
+#define X(OPID) case OPID: return launch_generic<OPID, 3>(g, cc, grid);
+    MDB_TERNARY_OPS(X)
+#undef X
+    default: return set_error(MDB_EINVAL, "unknown elementwise op %d", op);
+  }
+}
+
+}  // namespace mdb
+
+extern "C" {
+
+int mdb_elementwise(int op, const mdb_array* out, int n_in, const mdb_array* in) {
+  MDB_REQUIRE(n_in >= 1 && n_in <= 3, "elementwise takes 1..3 inputs, got %d", n_in);
+  return mdb::elementwise_impl(op, out, n_in, in);
+}
+
+int mdb_copy(const mdb_array* out, const mdb_array* in) {
+  return mdb::elementwise_impl(MDB_OP_COPY, out, 1, in);
+}
+
+int mdb_fill(const mdb_array* out, double value) {
+  mdb_array imm;
+  imm.ptr = nullptr; imm.dtype = MDB_F64; imm.ndim = 0; imm.imm = value;
+  imm.imm_i = (int64_t)value;
+  return mdb::elementwise_impl(MDB_OP_COPY, out, 1, &imm);
+}
+
+}  // extern "C"

@@ -1,0 +1,281 @@
+// Scalar semantics of every elementwise backend function, shared by the fast, generic and fused
+// reduce kernels.  Each op mirrors the NumPy function the reference binds in
+// minidiff/backend/numpy.py:19-95; the *_BWD forms evaluate the gradient call chains of
+// minidiff/ops/definitions.py step by step with explicitly rounded intrinsics (no FMA
+// contraction) so a fused launch gives the same bits as the chain of separate launches.
+#pragma once
+#include <math.h>
+#include <type_traits>
+
+#include "mdb_common.cuh"
+
+namespace mdb {
+
+template <typename T> __device__ __forceinline__ T mul_(T a, T b) { return a * b; }
+template <> __device__ __forceinline__ float mul_<float>(float a, float b) { return __fmul_rn(a, b); }
+template <> __device__ __forceinline__ double mul_<double>(double a, double b) { return __dmul_rn(a, b); }
+template <typename T> __device__ __forceinline__ T add_(T a, T b) { return a + b; }
+template <> __device__ __forceinline__ float add_<float>(float a, float b) { return __fadd_rn(a, b); }
+template <> __device__ __forceinline__ double add_<double>(double a, double b) { return __dadd_rn(a, b); }
+template <typename T> __device__ __forceinline__ T sub_(T a, T b) { return a - b; }
+template <> __device__ __forceinline__ float sub_<float>(float a, float b) { return __fsub_rn(a, b); }
+template <> __device__ __forceinline__ double sub_<double>(double a, double b) { return __dsub_rn(a, b); }
+template <typename T> __device__ __forceinline__ T div_(T a, T b) { return b == 0 ? T(0) : a / b; }
+template <> __device__ __forceinline__ float div_<float>(float a, float b) { return __fdiv_rn(a, b); }
+template <> __device__ __forceinline__ double div_<double>(double a, double b) { return __ddiv_rn(a, b); }
+
+// x**e.  NumPy's scalar-exponent fast paths (np.power(x, 2|1|0|0.5|-1) == x*x | x | 1 | sqrt |
+// 1/x bit-exactly: SURVEY finding 5) are honoured for every exponent value, immediate or not --
+// they are exact results, so applying them to array exponents as well only removes error.
+// The general case goes through double exp/log (|rel err| ~1e-14 => correctly rounded fp32 in
+// all but ~1e-7 of cases), far inside the 2-ulp budget that powf's documented 4 ulp would break.
+__device__ __forceinline__ float pow_f32(float x, float e) {
+  if (e == 2.0f) return __fmul_rn(x, x);
+  if (e == 1.0f) return x;
+  if (e == 0.0f) return 1.0f;
+  if (e == 0.5f) return sqrtf(x);
+  if (e == -1.0f) return __fdiv_rn(1.0f, x);
+  if (x > 0.0f && x < INFINITY && fabsf(e) < INFINITY) return (float)exp((double)e * log((double)x));
+  return powf(x, e);
+}
+__device__ __forceinline__ double pow_f64(double x, double e) {
+  if (e == 2.0) return x * x;
+  if (e == 1.0) return x;
+  if (e == 0.0) return 1.0;
+  if (e == 0.5) return sqrt(x);
+  if (e == -1.0) return 1.0 / x;
+  return pow(x, e);
+}
+__device__ __forceinline__ long long pow_i64(long long x, long long e) {
+  if (e < 0) return (x == 1) ? 1 : (x == -1 ? ((e & 1) ? -1 : 1) : 0);
+  long long r = 1;
+  while (e) {
+    if (e & 1) r *= x;
+    x *= x;
+    e >>= 1;
+  }
+  return r;
+}
+
+// Python-style modulo / floor division == npy_divmod (numpy/_core/src/npymath/npy_math_internal)
+template <typename T> __device__ __forceinline__ T fmod_py(T a, T b) {
+  if constexpr (std::is_integral_v<T>) {
+    if (b == 0) return 0;
+    T r = a % b;
+    if (r != 0 && ((r < 0) != (b < 0))) r += b;
+    return r;
+  } else {
+    T r = fmod(a, b);
+    if (b == 0) return r;  // nan
+    if (r != 0) {
+      if ((b < 0) != (r < 0)) r += b;
+    } else {
+      r = copysign(T(0), b);
+    }
+    return r;
+  }
+}
+template <typename T> __device__ __forceinline__ T floordiv_py(T a, T b) {
+  if constexpr (std::is_integral_v<T>) {
+    if (b == 0) return 0;
+    T q = a / b;
+    if ((a % b != 0) && ((a < 0) != (b < 0))) --q;
+    return q;
+  } else {
+    if (b == 0) return a / b;
+    T mod = fmod(a, b);
+    T div = (a - mod) / b;
+    if (mod != 0 && ((b < 0) != (mod < 0))) div -= T(1);
+    T fl;
+    if (div != 0) {
+      fl = floor(div);
+      if (div - fl > T(0.5)) fl += T(1);
+    } else {
+      fl = copysign(T(0), a / b);
+    }
+    return fl;
+  }
+}
+
+__host__ __device__ constexpr bool op_is_predicate(int op) {
+  return op == MDB_OP_LOGICAL_NOT || op == MDB_OP_ISNAN || (op >= MDB_OP_EQ && op <= MDB_OP_XOR);
+}
+__host__ __device__ constexpr bool op_float_only(int op) {
+  return (op >= MDB_OP_SIN && op <= MDB_OP_RECIP) || op == MDB_OP_ISNAN || op >= MDB_OP_SIN_BWD;
+}
+__host__ __device__ constexpr int op_arity(int op) {
+  if (op >= MDB_OP_SIN_BWD) return (op == MDB_OP_POW_BWD || op == MDB_OP_DIV_BWD_Y) ? 3 : 2;
+  return op < 32 ? 1 : (op < 64 ? 2 : 3);
+}
+
+// a, b, c: operands in backend-call order; d: host-computed auxiliary immediate (POW_BWD: the
+// exponent minus one, formed in double on the host exactly like Python forms `y - 1`).
+template <int OP, typename T>
+__device__ __forceinline__ T apply(T a, T b, T c, T d) {
+  constexpr bool I = std::is_integral_v<T>;
+  constexpr bool F32 = std::is_same_v<T, float>;
+  (void)b; (void)c; (void)d;
+  if constexpr (OP == MDB_OP_COPY) return a;
+  else if constexpr (OP == MDB_OP_NEG) return -a;
+  else if constexpr (OP == MDB_OP_ABS) { if constexpr (I) return a < 0 ? -a : a; else return fabs(a); }
+  else if constexpr (OP == MDB_OP_SIGN) {
+    if constexpr (!I) { if (a != a) return a; }
+    return T((a > 0) - (a < 0));
+  }
+  else if constexpr (OP == MDB_OP_CEIL) { if constexpr (I) return a; else return ceil(a); }
+  else if constexpr (OP == MDB_OP_FLOOR) { if constexpr (I) return a; else return floor(a); }
+  else if constexpr (OP == MDB_OP_SQUARE) return mul_(a, a);
+  else if constexpr (OP == MDB_OP_LOGICAL_NOT) return T(a == 0);
+  else if constexpr (OP == MDB_OP_INVERT) { if constexpr (I) return ~a; else return a; }
+  else if constexpr (OP == MDB_OP_ISNAN) return T(a != a);
+  else if constexpr (OP == MDB_OP_ADD) return add_(a, b);
+  else if constexpr (OP == MDB_OP_SUB) return sub_(a, b);
+  else if constexpr (OP == MDB_OP_MUL) return mul_(a, b);
+  else if constexpr (OP == MDB_OP_DIV) return div_(a, b);
+  else if constexpr (OP == MDB_OP_MOD) return fmod_py(a, b);
+  else if constexpr (OP == MDB_OP_FLOORDIV) return floordiv_py(a, b);
+  else if constexpr (OP == MDB_OP_MAXIMUM) { if constexpr (!I) { if (a != a) return a; if (b != b) return b; } return a > b ? a : b; }
+  else if constexpr (OP == MDB_OP_MINIMUM) { if constexpr (!I) { if (a != a) return a; if (b != b) return b; } return a < b ? a : b; }
+  else if constexpr (OP == MDB_OP_EQ) return T(a == b);
+  else if constexpr (OP == MDB_OP_NE) return T(a != b);
+  else if constexpr (OP == MDB_OP_GT) return T(a > b);
+  else if constexpr (OP == MDB_OP_GE) return T(a >= b);
+  else if constexpr (OP == MDB_OP_LT) return T(a < b);
+  else if constexpr (OP == MDB_OP_LE) return T(a <= b);
+  else if constexpr (OP == MDB_OP_AND) return T((a != 0) && (b != 0));
+  else if constexpr (OP == MDB_OP_OR) return T((a != 0) || (b != 0));
+  else if constexpr (OP == MDB_OP_XOR) return T((a != 0) != (b != 0));
+  else if constexpr (OP == MDB_OP_WHERE) return a != 0 ? b : c;
+  else if constexpr (OP == MDB_OP_CLIP) { T v = a; if (v < b) v = b; if (v > c) v = c; return v; }
+  else if constexpr (OP == MDB_OP_FMA) return add_(a, mul_(b, c));
+  else if constexpr (OP == MDB_OP_POW) {
+    if constexpr (I) return pow_i64(a, b);
+    else if constexpr (F32) return pow_f32(a, b);
+    else return pow_f64(a, b);
+  }
+  else if constexpr (I) return a;  // float-only ops are never instantiated for integers
+  else if constexpr (OP == MDB_OP_SIN) return sin(a);     // sinf for float (1 ulp), sin for double
+  else if constexpr (OP == MDB_OP_COS) return cos(a);
+  else if constexpr (OP == MDB_OP_EXP) return exp(a);
+  else if constexpr (OP == MDB_OP_LOG) return log(a);
+  else if constexpr (OP == MDB_OP_SQRT) return sqrt(a);
+  else if constexpr (OP == MDB_OP_RECIP) return div_(T(1), a);
+  // coverage ops: evaluated in double so the fp32 result is correctly rounded (CUDA's tanf/sinhf
+  // are 3-4 ulp, outside the 2-ulp budget)
+  else if constexpr (OP == MDB_OP_TAN) return (T)tan((double)a);
+  else if constexpr (OP == MDB_OP_SINH) return (T)sinh((double)a);
+  else if constexpr (OP == MDB_OP_COSH) return (T)cosh((double)a);
+  else if constexpr (OP == MDB_OP_TANH) return (T)tanh((double)a);
+  // fused backward chains: a = upstream grad, b = x (, c = y or exponent)
+  else if constexpr (OP == MDB_OP_SIN_BWD) return mul_(a, (T)cos(b));
+  else if constexpr (OP == MDB_OP_COS_BWD) return mul_(a, mul_(T(-1), (T)sin(b)));
+  else if constexpr (OP == MDB_OP_EXP_BWD) return mul_(a, (T)exp(b));
+  else if constexpr (OP == MDB_OP_LOG_BWD) return div_(a, b);
+  else if constexpr (OP == MDB_OP_TANH_BWD) { T ch = (T)cosh((double)b); return mul_(a, div_(T(1), mul_(ch, ch))); }
+  else if constexpr (OP == MDB_OP_POW_BWD) {
+    // (grad * y) * x**(y-1); c carries the scalar y, d carries y-1
+    T pw; if constexpr (F32) pw = pow_f32(b, d); else pw = pow_f64(b, d);
+    return mul_(mul_(a, c), pw);
+  }
+  else if constexpr (OP == MDB_OP_DIV_BWD_Y) return mul_(a, div_(mul_(T(-1), b), mul_(c, c)));
+  else if constexpr (OP == MDB_OP_RELU_MASK_BWD) return mul_(a, T(b > 0));
+  else return a;
+}
+
+// dtype-generic element access for the generic kernels (uniform switch: no divergence)
+template <typename T>
+__device__ __forceinline__ T load_as(const void* p, int dtype, int64_t off) {
+  switch (dtype) {
+    case MDB_F32: return (T)((const float*)p)[off];
+    case MDB_F64: return (T)((const double*)p)[off];
+    case MDB_I64: return (T)((const long long*)p)[off];
+    case MDB_I32: return (T)((const int*)p)[off];
+    case MDB_BOOL: case MDB_U8: return (T)((const unsigned char*)p)[off];
+    case MDB_I8: return (T)((const signed char*)p)[off];
+    case MDB_I16: return (T)((const short*)p)[off];
+    case MDB_U16: return (T)((const unsigned short*)p)[off];
+    case MDB_U32: return (T)((const unsigned int*)p)[off];
+    case MDB_U64: return (T)((const unsigned long long*)p)[off];
+    default: return T(0);
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store_as(void* p, int dtype, int64_t off, T v) {
+  switch (dtype) {
+    case MDB_F32: ((float*)p)[off] = (float)v; break;
+    case MDB_F64: ((double*)p)[off] = (double)v; break;
+    case MDB_I64: ((long long*)p)[off] = (long long)v; break;
+    case MDB_I32: ((int*)p)[off] = (int)v; break;
+    case MDB_BOOL: ((unsigned char*)p)[off] = (unsigned char)(v != T(0)); break;
+    case MDB_U8: ((unsigned char*)p)[off] = (unsigned char)(long long)v; break;
+    case MDB_I8: ((signed char*)p)[off] = (signed char)(long long)v; break;
+    case MDB_I16: ((short*)p)[off] = (short)(long long)v; break;
+    case MDB_U16: ((unsigned short*)p)[off] = (unsigned short)(long long)v; break;
+    case MDB_U32: ((unsigned int*)p)[off] = (unsigned int)(long long)v; break;
+    case MDB_U64: ((unsigned long long*)p)[off] = (unsigned long long)v; break;
+    default: break;
+  }
+}
+
+// ---- operand access of the fast (fp32-compute) kernels: <=3 collapsed dims, inner stride 0/1 ----
+enum { K_IMM = 0, K_F32 = 1, K_U8 = 2 };
+
+struct FastOperand {
+  const void* ptr;
+  int64_t s2, s1;  // outer strides (elements)
+  int s0;          // inner stride: 0 or 1
+  int kind;
+  float imm;
+};
+template <int VEC>
+__device__ __forceinline__ void fast_load(const FastOperand& o, uint32_t i2, uint32_t i1,
+                                          uint32_t col, float (&v)[VEC]) {
+  if (o.kind == K_IMM) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) v[j] = o.imm;
+    return;
+  }
+  int64_t off = (int64_t)i2 * o.s2 + (int64_t)i1 * o.s1;
+  if (o.kind == K_F32) {
+    const float* p = (const float*)o.ptr + off;
+    if (o.s0 == 0) {
+      float s = __ldg(p);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) v[j] = s;
+    } else if constexpr (VEC == 4) {
+      float4 q = __ldg((const float4*)(p + col));
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+      v[0] = __ldg(p + col);
+    }
+  } else {
+    const unsigned char* p = (const unsigned char*)o.ptr + off;
+    if (o.s0 == 0) {
+      float s = (float)__ldg(p);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) v[j] = s;
+    } else if constexpr (VEC == 4) {
+      uchar4 q = __ldg((const uchar4*)(p + col));
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+      v[0] = (float)__ldg(p + col);
+    }
+  }
+}
+
+// ---- host-side shape analysis shared by elementwise / reduce -----------------------------------
+struct Collapsed {
+  int ndim;                                  // collapsed rank (>= 1)
+  int64_t shape[MDB_MAX_DIMS];               // outermost first
+  int64_t ostr[MDB_MAX_DIMS];
+  int64_t istr[3][MDB_MAX_DIMS];
+};
+
+// Broadcast `in[k]` against out's shape, then drop extent-1 axes and merge neighbours that every
+// operand walks contiguously.  Returns non-zero (with the NumPy-style message) on shape mismatch.
+int collapse(const mdb_array* out, int n_in, const mdb_array* in, Collapsed* c);
+
+enum ComputeClass { CC_F32 = 0, CC_F64 = 1, CC_I64 = 2 };
+int compute_class(int op, const mdb_array* out, int n_in, const mdb_array* in);
+
+}  // namespace mdb

@@ -1,0 +1,118 @@
+// matmul (backend/numpy.py:84) and its two gradient GEMMs (ops/definitions.py:487-492):
+// dispatcher + the fp32 CUDA-core kernel used for shapes the tcgen05 path does not take
+// (small / unaligned operands, e.g. the reference tests' 10x30 @ 30x20).
+#include "mdb_common.cuh"
+
+namespace mdb {
+
+int gemm_tcgen05(const mdb_array* c, const mdb_array* a, const mdb_array* b, int accumulate);
+static int g_force_path = 0;
+
+// 64x64 output tile per CTA, K step 16, 4x4 micro-tile per thread; operands addressed through
+// (row, col) element strides so NN / NT / TN views need no copies.
+template <bool ACC>
+__global__ void __launch_bounds__(256) sgemm_simt(int M, int N, int K, const float* __restrict__ A,
+                                                  int64_t sam, int64_t sak,
+                                                  const float* __restrict__ B, int64_t sbk,
+                                                  int64_t sbn, float* C, int64_t scm, int64_t scn) {
+  constexpr int BM = 64, BN = 64, BK = 16;
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int tr = (tid / 16) * 4, tc = (tid % 16) * 4;
+  float acc[4][4] = {};
+  // loader mapping: pick the thread->element order that walks the operand's unit-stride axis
+  const bool a_k_fast = (sak == 1);
+  const bool b_n_fast = (sbn == 1);
+  for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int e = tid + i * 256;  // 1024 elements of the 64x16 A tile
+      int mm = a_k_fast ? e / BK : e % BM;
+      int kk = a_k_fast ? e % BK : e / BM;
+      int gm = m0 + mm, gk = k0 + kk;
+      As[kk][mm] = (gm < M && gk < K) ? A[(int64_t)gm * sam + (int64_t)gk * sak] : 0.f;
+      int nn = b_n_fast ? e % BN : e / BK;
+      int kb = b_n_fast ? e / BN : e % BK;
+      int gn = n0 + nn, gkb = k0 + kb;
+      Bs[kb][nn] = (gn < N && gkb < K) ? B[(int64_t)gkb * sbk + (int64_t)gn * sbn] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][tr + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tc + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int gm = m0 + tr + i, gn = n0 + tc + j;
+      if (gm < M && gn < N) {
+        float* p = C + (int64_t)gm * scm + (int64_t)gn * scn;
+        *p = ACC ? __fadd_rn(*p, acc[i][j]) : acc[i][j];
+      }
+    }
+}
+
+static int gemm_simt(const mdb_array* c, const mdb_array* a, const mdb_array* b, int accumulate) {
+  const int M = (int)a->shape[0], K = (int)a->shape[1], N = (int)b->shape[1];
+  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  if (accumulate)
+    sgemm_simt<true><<<grid, 256, 0, g_stream>>>(M, N, K, (const float*)a->ptr, a->strides[0],
+        a->strides[1], (const float*)b->ptr, b->strides[0], b->strides[1], (float*)c->ptr,
+        c->strides[0], c->strides[1]);
+  else
+    sgemm_simt<false><<<grid, 256, 0, g_stream>>>(M, N, K, (const float*)a->ptr, a->strides[0],
+        a->strides[1], (const float*)b->ptr, b->strides[0], b->strides[1], (float*)c->ptr,
+        c->strides[0], c->strides[1]);
+  MDB_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace mdb
+
+using namespace mdb;
+
+extern "C" {
+
+int mdb_gemm_config(int force_path) {
+  MDB_REQUIRE(force_path >= 0 && force_path <= 2, "force_path must be 0, 1 or 2");
+  g_force_path = force_path;
+  return 0;
+}
+
+int mdb_gemm(const mdb_array* c, const mdb_array* a, const mdb_array* b, int accumulate) {
+  MDB_TRY(ensure_init());
+  MDB_REQUIRE(a && b && c && a->ptr && b->ptr && c->ptr, "gemm: device arrays required");
+  MDB_REQUIRE(a->ndim == 2 && b->ndim == 2 && c->ndim == 2, "gemm: operands must be 2-D");
+  MDB_REQUIRE(a->dtype == MDB_F32 && b->dtype == MDB_F32 && c->dtype == MDB_F32,
+              "gemm: fp32 operands required");
+  if (a->shape[1] != b->shape[0])
+    return set_error(MDB_EINVAL, "matmul: Input operand 1 has a mismatch in its core dimension 0, "
+                     "with gufunc signature (n?,k),(k,m?)->(n?,m?) (size %lld is different from %lld)",
+                     (long long)b->shape[0], (long long)a->shape[1]);
+  MDB_REQUIRE(c->shape[0] == a->shape[0] && c->shape[1] == b->shape[1], "gemm: bad output shape");
+  MDB_REQUIRE(a->shape[0] < (1ll << 31) && a->shape[1] < (1ll << 31) && b->shape[1] < (1ll << 31),
+              "gemm: extents must fit in int32");
+  if (c->shape[0] == 0 || c->shape[1] == 0) return 0;
+  if (a->shape[1] == 0) return accumulate ? 0 : mdb_fill(c, 0.0);
+  if (g_force_path != 1) {
+    int rc = gemm_tcgen05(c, a, b, accumulate);
+    if (rc == 0) return 0;
+    if (rc != MDB_ENOTSUP || g_force_path == 2) return rc;
+  }
+  return gemm_simt(c, a, b, accumulate);
+}
+
+}  // extern "C"

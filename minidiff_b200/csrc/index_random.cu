@@ -1,0 +1,163 @@
+// Integer-array gather / scatter over the leading axis (getitem, __setitem__, index_add with
+// array keys: backend/numpy.py:73-75,105) and the counter-based device RNG behind rand / randn
+// (backend/numpy.py:131-134).  Coverage entry points, not on the BASELINE hot path.
+#include "ew_ops.cuh"
+
+namespace mdb {
+
+struct RowsParams {
+  char* a;              // gather: src / scatter: dst   (indexed side)
+  char* b;              // gather: out / scatter: src   (dense side, walked by i)
+  const long long* idx;
+  int64_t n_idx, a_rows, a_row_stride, b_row_stride;   // strides in elements
+  int nin;              // inner dims
+  int64_t ishape[MDB_MAX_DIMS], a_istr[MDB_MAX_DIMS], b_istr[MDB_MAX_DIMS];
+  int64_t inner, total;
+  int esize, dtype, mode;  // mode 0 gather, 1 scatter-assign, 2 scatter-add
+};
+
+__global__ void __launch_bounds__(256) rows_kernel(const RowsParams p) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < p.total; e += stride) {
+    int64_t i = e / p.inner, j = e - i * p.inner;
+    long long r = p.idx[i];
+    if (r < 0) r += p.a_rows;
+    r = r < 0 ? 0 : (r >= p.a_rows ? p.a_rows - 1 : r);
+    int64_t ao = r * p.a_row_stride, bo = i * p.b_row_stride;
+    for (int d = p.nin - 1; d >= 0; --d) {
+      int64_t q = j / p.ishape[d], k = j - q * p.ishape[d];
+      j = q;
+      ao += k * p.a_istr[d];
+      bo += k * p.b_istr[d];
+    }
+    if (p.mode == 2) {
+      switch (p.dtype) {
+        case MDB_F32: atomicAdd((float*)p.a + ao, ((const float*)p.b)[bo]); break;
+        case MDB_F64: atomicAdd((double*)p.a + ao, ((const double*)p.b)[bo]); break;
+        case MDB_I32: atomicAdd((int*)p.a + ao, ((const int*)p.b)[bo]); break;
+        case MDB_I64:
+          atomicAdd((unsigned long long*)p.a + ao, (unsigned long long)((const long long*)p.b)[bo]);
+          break;
+        default: break;
+      }
+      continue;
+    }
+    char* src = p.mode == 0 ? p.a + ao * p.esize : p.b + bo * p.esize;
+    char* dst = p.mode == 0 ? p.b + bo * p.esize : p.a + ao * p.esize;
+    switch (p.esize) {
+      case 1: *dst = *src; break;
+      case 2: *(short*)dst = *(const short*)src; break;
+      case 4: *(int*)dst = *(const int*)src; break;
+      default: *(long long*)dst = *(const long long*)src; break;
+    }
+  }
+}
+
+static int rows_op(const mdb_array* indexed, const mdb_array* dense, const mdb_array* idx, int mode) {
+  MDB_TRY(ensure_init());
+  MDB_REQUIRE(indexed && dense && idx && indexed->ptr && dense->ptr && idx->ptr, "device arrays required");
+  MDB_REQUIRE(idx->dtype == MDB_I64 && idx->ndim == 1 && (idx->shape[0] <= 1 || idx->strides[0] == 1),
+              "index vector must be contiguous int64");
+  MDB_REQUIRE(indexed->ndim >= 1 && dense->ndim == indexed->ndim, "gather/scatter: rank mismatch");
+  MDB_REQUIRE(indexed->dtype == dense->dtype, "gather/scatter: dtype mismatch");
+  MDB_REQUIRE(dense->shape[0] == idx->shape[0] || (mode != 0 && dense->shape[0] == 1),
+              "gather/scatter: leading extent must equal the number of indices");
+  if (mode == 2)
+    MDB_REQUIRE(indexed->dtype == MDB_F32 || indexed->dtype == MDB_F64 || indexed->dtype == MDB_I32 ||
+                indexed->dtype == MDB_I64, "index_add supports f32/f64/i32/i64");
+  RowsParams p;
+  p.a = (char*)indexed->ptr; p.b = (char*)dense->ptr; p.idx = (const long long*)idx->ptr;
+  p.n_idx = idx->shape[0]; p.a_rows = indexed->shape[0];
+  p.a_row_stride = indexed->strides[0];
+  p.b_row_stride = dense->shape[0] == 1 && idx->shape[0] != 1 ? 0 : dense->strides[0];
+  p.nin = indexed->ndim - 1; p.inner = 1;
+  for (int d = 0; d < p.nin; ++d) {
+    int64_t e = indexed->shape[d + 1];
+    MDB_REQUIRE(dense->shape[d + 1] == e || (mode != 0 && dense->shape[d + 1] == 1),
+                "gather/scatter: inner extents differ on axis %d", d + 1);
+    p.ishape[d] = e;
+    p.a_istr[d] = indexed->strides[d + 1];
+    p.b_istr[d] = dense->shape[d + 1] == e ? dense->strides[d + 1] : 0;
+    p.inner *= e;
+  }
+  p.total = p.n_idx * p.inner;
+  p.esize = dtype_size(indexed->dtype); p.dtype = indexed->dtype; p.mode = mode;
+  if (p.total == 0) return 0;
+  MDB_REQUIRE(p.a_rows > 0, "index out of bounds: indexed axis has extent 0");
+  rows_kernel<<<grid_for(p.total, 256), 256, 0, g_stream>>>(p);
+  MDB_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---- Philox4x32-10 (Salmon et al. 2011), one 128-bit block per 4 outputs ----------------------
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+  uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+  uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+__device__ __forceinline__ void philox4x32(uint64_t ctr, uint64_t seed, uint32_t (&out)[4]) {
+  uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) out[i] = c[i];
+}
+
+__global__ void __launch_bounds__(256) random_kernel(void* out, int dtype, int64_t n, int normal,
+                                                     uint64_t seed, uint64_t offset) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  // each iteration produces 2 values from one Philox block (64 random bits per value)
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b * 2 < n; b += stride) {
+    uint32_t r[4];
+    philox4x32((uint64_t)b + offset, seed, r);
+    double u0 = ((((uint64_t)r[0] << 32) | r[1]) >> 11) * (1.0 / 9007199254740992.0);
+    double u1 = ((((uint64_t)r[2] << 32) | r[3]) >> 11) * (1.0 / 9007199254740992.0);
+    double v0 = u0, v1 = u1;
+    if (normal) {  // Box-Muller on (0,1] x [0,1)
+      double rad = sqrt(-2.0 * log(1.0 - u0));
+      double s, c;
+      sincospi(2.0 * u1, &s, &c);
+      v0 = rad * c; v1 = rad * s;
+    }
+    int64_t i = b * 2;
+    store_as<double>(out, dtype, i, v0);
+    if (i + 1 < n) store_as<double>(out, dtype, i + 1, v1);
+  }
+}
+
+}  // namespace mdb
+
+using namespace mdb;
+
+extern "C" {
+
+int mdb_gather_rows(const mdb_array* out, const mdb_array* src, const mdb_array* idx) {
+  return rows_op(src, out, idx, 0);
+}
+int mdb_scatter_rows(const mdb_array* dst, const mdb_array* src, const mdb_array* idx, int add) {
+  return rows_op(dst, src, idx, add ? 2 : 1);
+}
+
+int mdb_random(const mdb_array* out, int normal, uint64_t seed, uint64_t offset) {
+  MDB_TRY(ensure_init());
+  MDB_REQUIRE(out && out->ptr && (out->dtype == MDB_F32 || out->dtype == MDB_F64),
+              "random: contiguous f32/f64 output required");
+  int64_t n = numel(out), st = 1;
+  for (int d = out->ndim - 1; d >= 0; --d) {
+    MDB_REQUIRE(out->shape[d] == 1 || out->strides[d] == st, "random: output must be contiguous");
+    st *= out->shape[d];
+  }
+  if (n == 0) return 0;
+  random_kernel<<<grid_for((n + 1) / 2, 256), 256, 0, g_stream>>>(out->ptr, out->dtype, n, normal,
+                                                                 seed, offset);
+  MDB_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // extern "C"

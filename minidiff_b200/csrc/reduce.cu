@@ -1,0 +1,584 @@
+// Reductions of the backend boundary: sum/mean/max/min/prod/any/all/argmax/argmin
+// (backend/numpy.py:20-57) and the fused "gradient -> un-broadcast -> accumulate" form that
+// replaces grad-lambda + md.unbroadcast + `grad + new` (topology.py:93-104,
+// ops/definitions.py:157-183) with a single pass.
+//
+// Fast fp32 kernels (sum/mean/max/min over one run of adjacent axes):
+//   red_row_warp / red_row_cta : reduce the innermost (contiguous) run -> warp-shuffle + shared-memory
+//                                block reduction, rows split across CTAs when there are few rows
+//   red_col                    : reduce a middle/outer run while the inner axis stays contiguous;
+//                                32x8 thread tiles, 128-bit column vectors, rows split over grid.y
+// Both are two-pass when split (partials -> same kernel again), so results are deterministic.
+// Everything else (other dtypes, scattered axes, arg-reductions) takes the generic kernel.
+#include <algorithm>
+#include <limits>
+
+#include "ew_ops.cuh"
+
+namespace mdb {
+
+int elementwise_impl(int op, const mdb_array* out, int n_in, const mdb_array* in);
+
+enum { R_SUM = 0, R_MAX = 1, R_MIN = 2 };
+
+template <int RED> __device__ __forceinline__ float red_identity() {
+  if constexpr (RED == R_SUM) return 0.f;
+  else if constexpr (RED == R_MAX) return -INFINITY;
+  else return INFINITY;
+}
+template <int RED> __device__ __forceinline__ float red_combine(float a, float b) {
+  if constexpr (RED == R_SUM) return __fadd_rn(a, b);
+  else if constexpr (RED == R_MAX) { if (a != a) return a; if (b != b) return b; return a > b ? a : b; }
+  else { if (a != a) return a; if (b != b) return b; return a < b ? a : b; }
+}
+template <int RED> __device__ __forceinline__ float warp_reduce(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = red_combine<RED>(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+struct RedParams {
+  FastOperand in[3];
+  float aux;
+  float* dst;              // final output or partial buffer
+  int64_t os2, os1;        // output strides over (i2, i1) [row kernels] / (i2) + unit inner [col]
+  uint32_t d1;             // extent of collapsed dim 1 (row kernels: rows = d2*d1)
+  FastDiv div_d1;
+  uint32_t L;              // reduced extent in VEC units (row) / reduced rows (col)
+  uint32_t seg;            // work per split, same units as L
+  uint32_t nsplit;
+  uint32_t I;              // col kernel: inner extent (elements)
+  uint32_t rows;           // row kernels: number of rows
+  int to_partial;          // 1: dst is the partial buffer [.., nsplit, ..]
+  int accumulate;          // final write: dst = dst + result
+  float divisor;           // > 0: mean -> result / divisor
+};
+
+template <int OP, int NIN, int VEC>
+__device__ __forceinline__ void load_apply(const RedParams& p, uint32_t i2, uint32_t i1,
+                                           uint32_t col, float (&r)[VEC]) {
+  float v[3][VEC];
+#pragma unroll
+  for (int k = 0; k < NIN; ++k) fast_load<VEC>(p.in[k], i2, i1, col, v[k]);
+#pragma unroll
+  for (int j = 0; j < VEC; ++j)
+    r[j] = apply<OP, float>(v[0][j], NIN > 1 ? v[1][j] : 0.f, NIN > 2 ? v[2][j] : 0.f, p.aux);
+}
+
+__device__ __forceinline__ void final_store(const RedParams& p, float* where, float v) {
+  if (p.divisor > 0.f) v = __fdiv_rn(v, p.divisor);
+  if (p.accumulate) v = __fadd_rn(*where, v);
+  *where = v;
+}
+
+// one warp per row (short rows, many rows)
+template <int OP, int NIN, int RED, int VEC>
+__global__ void __launch_bounds__(256) red_row_warp(const RedParams p) {
+  const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  for (uint32_t row = blockIdx.x * 8 + wib; row < p.rows; row += gridDim.x * 8) {
+    uint32_t i2, i1;
+    p.div_d1.divmod(row, i2, i1);
+    float acc[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] = red_identity<RED>();
+    for (uint32_t c = lane; c < p.L; c += 32) {
+      float r[VEC];
+      load_apply<OP, NIN, VEC>(p, i2, i1, c * VEC, r);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) acc[j] = red_combine<RED>(acc[j], r[j]);
+    }
+    float a = acc[0];
+    if constexpr (VEC == 4)
+      a = red_combine<RED>(red_combine<RED>(acc[0], acc[1]), red_combine<RED>(acc[2], acc[3]));
+    a = warp_reduce<RED>(a);
+    if (lane == 0) final_store(p, p.dst + (int64_t)i2 * p.os2 + (int64_t)i1 * p.os1, a);
+  }
+}
+
+// one CTA per (row, split): long rows
+template <int OP, int NIN, int RED, int VEC>
+__global__ void __launch_bounds__(256) red_row_cta(const RedParams p) {
+  constexpr int U = 4;
+  __shared__ float sm[8];
+  const uint32_t row = blockIdx.x, split = blockIdx.y;
+  uint32_t i2, i1;
+  p.div_d1.divmod(row, i2, i1);
+  const uint32_t start = split * p.seg;
+  const uint32_t end = min(start + p.seg, p.L);
+  float acc[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) acc[j] = red_identity<RED>();
+  for (uint32_t c = start + threadIdx.x; c < end; c += 256 * U) {
+    float r[U][VEC];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (c + u * 256 < end) load_apply<OP, NIN, VEC>(p, i2, i1, (c + u * 256) * VEC, r[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (c + u * 256 < end) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] = red_combine<RED>(acc[j], r[u][j]);
+      }
+  }
+  float a = acc[0];
+  if constexpr (VEC == 4)
+    a = red_combine<RED>(red_combine<RED>(acc[0], acc[1]), red_combine<RED>(acc[2], acc[3]));
+  a = warp_reduce<RED>(a);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float b = threadIdx.x < 8 ? sm[threadIdx.x] : red_identity<RED>();
+    b = warp_reduce<RED>(b);
+    if (threadIdx.x == 0) {
+      if (p.to_partial) p.dst[(int64_t)row * p.nsplit + split] = b;
+      else final_store(p, p.dst + (int64_t)i2 * p.os2 + (int64_t)i1 * p.os1, b);
+    }
+  }
+}
+
+// reduce over collapsed dim 1 (rows), keep dim 2 (outer) and dim 0 (inner, contiguous)
+template <int OP, int NIN, int RED, int VEC>
+__global__ void __launch_bounds__(256) red_col(const RedParams p) {
+  constexpr int U = 4;
+  __shared__ float sm[8][32][VEC];
+  const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const uint32_t col = (blockIdx.x * 32 + tx) * VEC;
+  const uint32_t split = blockIdx.y, o2 = blockIdx.z;
+  const bool active = col < p.I;
+  const uint32_t r0 = split * p.seg, r1 = min(r0 + p.seg, p.L);
+  float acc[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) acc[j] = red_identity<RED>();
+  if (active) {
+    for (uint32_t r = r0 + ty; r < r1; r += 8 * U) {
+      float v[U][VEC];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (r + u * 8 < r1) load_apply<OP, NIN, VEC>(p, o2, r + u * 8, col, v[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (r + u * 8 < r1) {
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) acc[j] = red_combine<RED>(acc[j], v[u][j]);
+        }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) sm[ty][tx][j] = acc[j];
+  __syncthreads();
+  if (ty == 0 && active) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float a = sm[0][tx][j];
+#pragma unroll
+      for (int t = 1; t < 8; ++t) a = red_combine<RED>(a, sm[t][tx][j]);
+      if (p.to_partial) p.dst[((int64_t)o2 * p.nsplit + split) * p.I + col + j] = a;
+      else final_store(p, p.dst + (int64_t)o2 * p.os2 + col + j, a);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic fallback: one thread per output element, any dtype / strides / axes
+// ------------------------------------------------------------------------------------------------
+struct GenRedParams {
+  const void* in;
+  void* out;
+  int in_dtype, out_dtype, red;
+  int nk, nr;                              // kept / reduced axis counts
+  int64_t kshape[MDB_MAX_DIMS], kistr[MDB_MAX_DIMS], kostr[MDB_MAX_DIMS];
+  int64_t rshape[MDB_MAX_DIMS], ristr[MDB_MAX_DIMS];
+  int64_t n_out, n_red;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128) red_generic(const GenRedParams p) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < p.n_out; o += stride) {
+    int64_t rem = o, ibase = 0, obase = 0;
+    for (int d = p.nk - 1; d >= 0; --d) {
+      int64_t q = rem / p.kshape[d], idx = rem - q * p.kshape[d];
+      rem = q;
+      ibase += idx * p.kistr[d];
+      obase += idx * p.kostr[d];
+    }
+    T acc = T(0);
+    long long best = 0;
+    bool first = true;
+    if (p.red == MDB_RED_PROD || p.red == MDB_RED_ALL) acc = T(1);
+    for (int64_t r = 0; r < p.n_red; ++r) {
+      int64_t rr = r, off = ibase;
+      for (int d = p.nr - 1; d >= 0; --d) {
+        int64_t q = rr / p.rshape[d], idx = rr - q * p.rshape[d];
+        rr = q;
+        off += idx * p.ristr[d];
+      }
+      T v = load_as<T>(p.in, p.in_dtype, off);
+      switch (p.red) {
+        case MDB_RED_SUM: case MDB_RED_MEAN: acc += v; break;
+        case MDB_RED_PROD: acc *= v; break;
+        case MDB_RED_ANY: acc = T((acc != T(0)) || (v != T(0))); break;
+        case MDB_RED_ALL: acc = T((acc != T(0)) && (v != T(0))); break;
+        case MDB_RED_MAX:
+          if (first || (acc == acc && (v > acc || v != v))) acc = v;
+          break;
+        case MDB_RED_MIN:
+          if (first || (acc == acc && (v < acc || v != v))) acc = v;
+          break;
+        case MDB_RED_ARGMAX:
+          if (first || (acc == acc && (v > acc || v != v))) { acc = v; best = r; }
+          break;
+        case MDB_RED_ARGMIN:
+          if (first || (acc == acc && (v < acc || v != v))) { acc = v; best = r; }
+          break;
+      }
+      first = false;
+    }
+    if (p.red == MDB_RED_MEAN) acc = acc / (T)p.n_red;
+    if (p.red == MDB_RED_ARGMAX || p.red == MDB_RED_ARGMIN)
+      store_as<long long>(p.out, p.out_dtype, obase, best);
+    else
+      store_as<T>(p.out, p.out_dtype, obase, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host logic
+// ------------------------------------------------------------------------------------------------
+struct RedPlan {          // iteration space collapsed to [d2, d1, d0]
+  int pattern;            // 0: reduce d0 (row); 1: reduce d1 keeping d0 (col); -1: none
+  int64_t d2, d1, d0;
+  int64_t istr[3][3];     // per input: strides over (d2, d1, d0)
+  int64_t ostr[3];        // output strides over (d2, d1, d0) (0 on reduced dims)
+};
+
+// full: iteration shape; red[d]: axis reduced; istr[k][d] / ostr[d]: strides (0 where broadcast)
+static bool plan_fast(int nd, const int64_t* full, const bool* red, int n_in,
+                      const int64_t (*istr)[MDB_MAX_DIMS], const int64_t* ostr, RedPlan* pl) {
+  int64_t shape[MDB_MAX_DIMS], is[3][MDB_MAX_DIMS], os[MDB_MAX_DIMS];
+  bool rf[MDB_MAX_DIMS];
+  int m = 0;
+  for (int d = 0; d < nd; ++d) {
+    if (full[d] == 1) continue;
+    if (m > 0 && rf[m - 1] == red[d]) {
+      bool merge = red[d] || os[m - 1] == ostr[d] * full[d];
+      for (int k = 0; merge && k < n_in; ++k) merge = is[k][m - 1] == istr[k][d] * full[d];
+      if (merge) {
+        shape[m - 1] *= full[d];
+        os[m - 1] = ostr[d];
+        for (int k = 0; k < n_in; ++k) is[k][m - 1] = istr[k][d];
+        continue;
+      }
+    }
+    shape[m] = full[d]; rf[m] = red[d]; os[m] = red[d] ? 0 : ostr[d];
+    for (int k = 0; k < n_in; ++k) is[k][m] = istr[k][d];
+    ++m;
+  }
+  if (m == 0 || m > 3) return false;
+  // recognise [R], [K,R], [K,K,R] (row) and [R,K], [K,R,K] (col)
+  int pattern = -1;
+  if (rf[m - 1]) {
+    pattern = 0;
+    for (int d = 0; d < m - 1; ++d) if (rf[d]) return false;
+  } else if (m >= 2 && rf[m - 2]) {
+    pattern = 1;
+    if (m == 3 && rf[0]) return false;
+  } else {
+    return false;
+  }
+  pl->pattern = pattern;
+  int64_t sh3[3] = {1, 1, 1};
+  for (int k = 0; k < 3; ++k) for (int j = 0; j < 3; ++j) pl->istr[k][j] = 0;
+  pl->ostr[0] = pl->ostr[1] = pl->ostr[2] = 0;
+  for (int d = 0; d < m; ++d) {
+    int slot = 3 - m + d;
+    sh3[slot] = shape[d];
+    pl->ostr[slot] = os[d];
+    for (int k = 0; k < n_in; ++k) pl->istr[k][slot] = is[k][d];
+  }
+  pl->d2 = sh3[0]; pl->d1 = sh3[1]; pl->d0 = sh3[2];
+  for (int k = 0; k < n_in; ++k) {
+    int64_t s0 = pl->istr[k][2];
+    if (s0 != 0 && s0 != 1) return false;
+  }
+  if (pattern == 1 && pl->ostr[2] != 1) return false;
+  return true;
+}
+
+static bool aligned16(const void* p, size_t a) { return ((uintptr_t)p % a) == 0; }
+
+#define MDB_FUSED_RED_OPS(X)                                                                    \
+  X(MDB_OP_COPY, 1) X(MDB_OP_NEG, 1) X(MDB_OP_MUL, 2) X(MDB_OP_DIV, 2) X(MDB_OP_SIN_BWD, 2)     \
+  X(MDB_OP_COS_BWD, 2) X(MDB_OP_EXP_BWD, 2) X(MDB_OP_LOG_BWD, 2) X(MDB_OP_RELU_MASK_BWD, 2)     \
+  X(MDB_OP_POW_BWD, 3) X(MDB_OP_DIV_BWD_Y, 3)
+
+template <int OP, int NIN, int RED>
+static int launch_fast_red(const RedPlan& pl, RedParams p, int vec, float* out, bool accumulate,
+                           float divisor) {
+  p.accumulate = accumulate; p.divisor = divisor;
+  if (pl.pattern == 0) {
+    const int64_t rows = pl.d2 * pl.d1;
+    const uint32_t L = (uint32_t)(pl.d0 / vec);
+    p.rows = (uint32_t)rows; p.L = L; p.d1 = (uint32_t)pl.d1; p.div_d1 = FastDiv((uint32_t)pl.d1);
+    p.os2 = pl.ostr[0]; p.os1 = pl.ostr[1];
+    if (pl.d0 < 2048) {
+      p.dst = out; p.to_partial = 0; p.nsplit = 1; p.seg = L;
+      int grid = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)g_sm_count * 16);
+      if (vec == 4) red_row_warp<OP, NIN, RED, 4><<<grid, 256, 0, g_stream>>>(p);
+      else red_row_warp<OP, NIN, RED, 1><<<grid, 256, 0, g_stream>>>(p);
+      MDB_CHECK_LAUNCH();
+      return 0;
+    }
+    // long rows: split so that >= ~4 CTAs per SM exist, each split >= 4096 work items
+    int64_t want = ((int64_t)g_sm_count * 4 + rows - 1) / rows;
+    int64_t maxsplit = std::max<int64_t>(1, L / 4096);
+    uint32_t nsplit = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(std::min(want, maxsplit), 65535));
+    uint32_t seg = (L + nsplit - 1) / nsplit;
+    nsplit = (L + seg - 1) / seg;
+    p.seg = seg; p.nsplit = nsplit;
+    TempBuf tmp;
+    if (nsplit > 1) {
+      MDB_TRY(tmp.alloc((size_t)rows * nsplit * sizeof(float)));
+      p.dst = (float*)tmp.ptr; p.to_partial = 1;
+    } else {
+      p.dst = out; p.to_partial = 0;
+    }
+    dim3 grid((unsigned)rows, nsplit);
+    if (vec == 4) red_row_cta<OP, NIN, RED, 4><<<grid, 256, 0, g_stream>>>(p);
+    else red_row_cta<OP, NIN, RED, 1><<<grid, 256, 0, g_stream>>>(p);
+    MDB_CHECK_LAUNCH();
+    if (nsplit > 1) {  // second pass over the [rows, nsplit] partials
+      RedParams q = p;
+      q.in[0].ptr = tmp.ptr; q.in[0].kind = K_F32; q.in[0].s0 = 1;
+      q.in[0].s1 = nsplit; q.in[0].s2 = (int64_t)nsplit * pl.d1;
+      q.L = nsplit; q.seg = nsplit; q.nsplit = 1; q.dst = out; q.to_partial = 0;
+      int grid2 = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)g_sm_count * 16);
+      red_row_warp<MDB_OP_COPY, 1, RED, 1><<<grid2, 256, 0, g_stream>>>(q);
+      MDB_CHECK_LAUNCH();
+    }
+    return 0;
+  }
+  // column pattern
+  const int64_t R = pl.d1, I = pl.d0, O2 = pl.d2;
+  p.L = (uint32_t)R; p.I = (uint32_t)I; p.os2 = pl.ostr[0];
+  const int tile = 32 * vec;
+  const int64_t gx = (I + tile - 1) / tile;
+  int64_t want = ((int64_t)g_sm_count * 4 + gx * O2 - 1) / (gx * O2);
+  int64_t maxsplit = std::max<int64_t>(1, R / 64);
+  uint32_t nsplit = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(std::min(want, maxsplit), 1024));
+  uint32_t seg = (uint32_t)((R + nsplit - 1) / nsplit);
+  nsplit = (uint32_t)((R + seg - 1) / seg);
+  p.seg = seg; p.nsplit = nsplit;
+  TempBuf tmp;
+  if (nsplit > 1) {
+    MDB_TRY(tmp.alloc((size_t)O2 * nsplit * I * sizeof(float)));
+    p.dst = (float*)tmp.ptr; p.to_partial = 1;
+  } else {
+    p.dst = out; p.to_partial = 0;
+  }
+  dim3 grid((unsigned)gx, nsplit, (unsigned)O2);
+  if (vec == 4) red_col<OP, NIN, RED, 4><<<grid, 256, 0, g_stream>>>(p);
+  else red_col<OP, NIN, RED, 1><<<grid, 256, 0, g_stream>>>(p);
+  MDB_CHECK_LAUNCH();
+  if (nsplit > 1) {
+    RedParams q = p;
+    q.in[0].ptr = tmp.ptr; q.in[0].kind = K_F32; q.in[0].s0 = 1;
+    q.in[0].s1 = I; q.in[0].s2 = (int64_t)nsplit * I;
+    q.L = nsplit; q.seg = nsplit; q.nsplit = 1; q.dst = out; q.to_partial = 0;
+    const bool v4 = (vec == 4);  // partial rows are 16B aligned iff I % 4 == 0 (true when vec == 4)
+    dim3 grid2((unsigned)gx, 1, (unsigned)O2);
+    if (v4) red_col<MDB_OP_COPY, 1, RED, 4><<<grid2, 256, 0, g_stream>>>(q);
+    else red_col<MDB_OP_COPY, 1, RED, 1><<<grid2, 256, 0, g_stream>>>(q);
+    MDB_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+static int generic_reduce(int red, const mdb_array* out, const mdb_array* in, uint32_t axis_mask) {
+  GenRedParams g;
+  g.in = in->ptr; g.out = out->ptr; g.in_dtype = in->dtype; g.out_dtype = out->dtype; g.red = red;
+  g.nk = g.nr = 0; g.n_out = 1; g.n_red = 1;
+  for (int d = 0; d < in->ndim; ++d) {
+    if (axis_mask & (1u << d)) {
+      g.rshape[g.nr] = in->shape[d]; g.ristr[g.nr] = in->strides[d]; ++g.nr;
+      g.n_red *= in->shape[d];
+    } else {
+      g.kshape[g.nk] = in->shape[d]; g.kistr[g.nk] = in->strides[d];
+      g.kostr[g.nk] = out->strides[d]; ++g.nk;
+      g.n_out *= in->shape[d];
+    }
+  }
+  if (g.n_out == 0) return 0;
+  if (g.n_red == 0 && (red == MDB_RED_MAX || red == MDB_RED_MIN || red == MDB_RED_ARGMAX ||
+                       red == MDB_RED_ARGMIN))
+    return set_error(MDB_EINVAL, "zero-size array to reduction operation which has no identity");
+  int grid = grid_for(g.n_out, 128);
+  const bool int_acc = !dtype_is_float(in->dtype) &&
+                       (red != MDB_RED_MEAN) && !dtype_is_float(out->dtype);
+  if (int_acc) red_generic<long long><<<grid, 128, 0, g_stream>>>(g);
+  else red_generic<double><<<grid, 128, 0, g_stream>>>(g);
+  MDB_CHECK_LAUNCH();
+  return 0;
+}
+
+// shared driver for mdb_reduce (op = COPY) and mdb_elementwise_reduce
+static int reduce_driver(int op, int red, const mdb_array* out, int n_in, const mdb_array* in,
+                         const int64_t* full, const bool* redax, int nd, bool accumulate) {
+  int64_t istr[3][MDB_MAX_DIMS], ostr[MDB_MAX_DIMS];
+  int64_t n_red = 1, n_out = 1;
+  for (int d = 0; d < nd; ++d) {
+    ostr[d] = redax[d] ? 0 : (out->shape[d] == 1 ? 0 : out->strides[d]);
+    if (redax[d]) n_red *= full[d]; else n_out *= full[d];
+  }
+  bool fast_ok = out->dtype == MDB_F32 && (red == MDB_RED_SUM || red == MDB_RED_MEAN ||
+                                            red == MDB_RED_MAX || red == MDB_RED_MIN);
+  for (int k = 0; k < n_in; ++k) {
+    const mdb_array& a = in[k];
+    if (a.ptr == nullptr) { for (int d = 0; d < nd; ++d) istr[k][d] = 0; continue; }
+    fast_ok = fast_ok && (a.dtype == MDB_F32 || ((a.dtype == MDB_BOOL || a.dtype == MDB_U8) && op != MDB_OP_COPY));
+    int lead = nd - a.ndim;
+    MDB_REQUIRE(lead >= 0, "reduce: input %d has more dims than the iteration space", k);
+    for (int d = 0; d < nd; ++d) {
+      if (d < lead) { istr[k][d] = 0; continue; }
+      int64_t ext = a.shape[d - lead];
+      MDB_REQUIRE(ext == full[d] || ext == 1, "operands could not be broadcast together: extent "
+                  "%lld vs %lld on axis %d", (long long)ext, (long long)full[d], d);
+      istr[k][d] = (ext == 1) ? 0 : a.strides[d - lead];
+    }
+  }
+  if (n_out == 0) return 0;
+  RedPlan pl;
+  fast_ok = fast_ok && n_red > 0 && n_red < (int64_t(1) << 31) && n_out < (int64_t(1) << 31) &&
+            plan_fast(nd, full, redax, n_in, istr, ostr, &pl);
+  if (fast_ok && pl.pattern == 1 && pl.d2 > 65535) fast_ok = false;
+  if (fast_ok) {
+    RedParams p;
+    p.aux = 0.f;
+    bool v4 = pl.d0 % 4 == 0;
+    for (int k = 0; k < n_in; ++k) {
+      FastOperand& o = p.in[k];
+      o.ptr = in[k].ptr; o.imm = (float)in[k].imm;
+      o.kind = in[k].ptr == nullptr ? K_IMM : (in[k].dtype == MDB_F32 ? K_F32 : K_U8);
+      o.s2 = pl.istr[k][0]; o.s1 = pl.istr[k][1]; o.s0 = (int)pl.istr[k][2];
+      if (o.kind != K_IMM && o.s0 == 1) {
+        size_t esz = o.kind == K_F32 ? 4 : 1;
+        v4 = v4 && aligned16(o.ptr, 4 * esz) && o.s1 % 4 == 0 && o.s2 % 4 == 0;
+      }
+    }
+    if (op == MDB_OP_POW_BWD) {
+      MDB_REQUIRE(in[2].ptr == nullptr, "POW_BWD needs an immediate exponent");
+      p.aux = (float)(in[2].imm - 1.0);
+    }
+    if (pl.pattern == 1) v4 = v4 && aligned16(out->ptr, 16) && pl.ostr[0] % 4 == 0;
+    const int vec = v4 ? 4 : 1;
+    float divisor = red == MDB_RED_MEAN ? (float)n_red : 0.f;
+    int r = red == MDB_RED_MAX ? R_MAX : (red == MDB_RED_MIN ? R_MIN : R_SUM);
+    float* o = (float*)out->ptr;
+    if (op == MDB_OP_COPY) {
+      if (r == R_SUM) return launch_fast_red<MDB_OP_COPY, 1, R_SUM>(pl, p, vec, o, accumulate, divisor);
+      if (r == R_MAX) return launch_fast_red<MDB_OP_COPY, 1, R_MAX>(pl, p, vec, o, accumulate, divisor);
+      return launch_fast_red<MDB_OP_COPY, 1, R_MIN>(pl, p, vec, o, accumulate, divisor);
+    }
+    if (r == R_SUM) {
+      switch (op) {
+#define X(OPID, N) case OPID: return launch_fast_red<OPID, N, R_SUM>(pl, p, vec, o, accumulate, divisor);
+        MDB_FUSED_RED_OPS(X)
+#undef X
+        default: break;
+      }
+    }
+  }
+  // ---- fallback: materialise the elementwise result (if any), then generic / staged reduce
+  mdb_array src;
+  TempBuf tmp;
+  if (op != MDB_OP_COPY || n_in != 1 || in[0].ptr == nullptr || in[0].ndim != nd) {
+    int64_t n = n_red * n_out;
+    src.dtype = out->dtype == MDB_BOOL ? in[0].dtype : out->dtype;
+    if (red == MDB_RED_ARGMAX || red == MDB_RED_ARGMIN || red == MDB_RED_ANY || red == MDB_RED_ALL)
+      src.dtype = in[0].dtype;
+    MDB_TRY(tmp.alloc((size_t)std::max<int64_t>(n, 1) * dtype_size(src.dtype)));
+    src.ptr = tmp.ptr; src.ndim = nd; src.imm = 0; src.imm_i = 0;
+    int64_t st = 1;
+    for (int d = nd - 1; d >= 0; --d) { src.shape[d] = full[d]; src.strides[d] = st; st *= full[d]; }
+    MDB_TRY(elementwise_impl(op, &src, n_in, in));
+  } else {
+    src = in[0];
+    for (int d = 0; d < nd; ++d) if (src.shape[d] != full[d]) { src.shape[d] = full[d]; src.strides[d] = 0; }
+  }
+  uint32_t mask = 0;
+  for (int d = 0; d < nd; ++d) if (redax[d]) mask |= 1u << d;
+  if (!accumulate) return generic_reduce(red, out, &src, mask);
+  // accumulate: reduce into a temp shaped like out, then out += temp
+  TempBuf t2;
+  mdb_array o2 = *out;
+  MDB_TRY(t2.alloc((size_t)std::max<int64_t>(n_out, 1) * dtype_size(out->dtype)));
+  o2.ptr = t2.ptr;
+  int64_t st = 1;
+  for (int d = nd - 1; d >= 0; --d) { o2.strides[d] = st; st *= o2.shape[d]; }
+  MDB_TRY(generic_reduce(red, &o2, &src, mask));
+  mdb_array pair[2] = {*out, o2};
+  return elementwise_impl(MDB_OP_ADD, out, 2, pair);
+}
+
+}  // namespace mdb
+
+using namespace mdb;
+
+extern "C" {
+
+int mdb_reduce(int red, const mdb_array* out, const mdb_array* in, uint32_t axis_mask) {
+  MDB_TRY(ensure_init());
+  MDB_REQUIRE(in && in->ptr && out && out->ptr, "reduce: device arrays required");
+  MDB_REQUIRE(out->ndim == in->ndim, "reduce: out must be given in keepdims form");
+  const int nd = in->ndim;
+  bool redax[MDB_MAX_DIMS];
+  int64_t full[MDB_MAX_DIMS];
+  for (int d = 0; d < nd; ++d) {
+    redax[d] = (axis_mask >> d) & 1u;
+    full[d] = in->shape[d];
+    MDB_REQUIRE(out->shape[d] == (redax[d] ? 1 : in->shape[d]), "reduce: bad output extent on axis %d", d);
+  }
+  if (nd == 0) return elementwise_impl(MDB_OP_COPY, out, 1, in);
+  return reduce_driver(MDB_OP_COPY, red, out, 1, in, full, redax, nd, false);
+}
+
+int mdb_elementwise_reduce(int op, const mdb_array* out, int n_in, const mdb_array* in,
+                           int accumulate) {
+  MDB_TRY(ensure_init());
+  MDB_REQUIRE(out && out->ptr && n_in >= 1 && n_in <= 3, "elementwise_reduce: bad arguments");
+  MDB_REQUIRE(n_in == op_arity(op), "op %d takes %d inputs, got %d", op, op_arity(op), n_in);
+  // iteration space = broadcast of all inputs; out is right-aligned against it, axes where out's
+  // extent is 1 (or missing) but the iteration extent is larger are summed away
+  int nd = out->ndim;
+  for (int k = 0; k < n_in; ++k) if (in[k].ptr && in[k].ndim > nd) nd = in[k].ndim;
+  MDB_REQUIRE(nd <= MDB_MAX_DIMS, "too many dimensions");
+  int64_t full[MDB_MAX_DIMS];
+  for (int d = 0; d < nd; ++d) full[d] = 1;
+  for (int k = 0; k < n_in; ++k) {
+    if (!in[k].ptr) continue;
+    int lead = nd - in[k].ndim;
+    for (int d = 0; d < in[k].ndim; ++d) {
+      int64_t e = in[k].shape[d];
+      if (e != 1) {
+        MDB_REQUIRE(full[lead + d] == 1 || full[lead + d] == e,
+                    "operands could not be broadcast together on axis %d", lead + d);
+        full[lead + d] = e;
+      }
+    }
+  }
+  mdb_array o = *out;  // right-align out
+  const int olead = nd - out->ndim;
+  bool redax[MDB_MAX_DIMS];
+  for (int d = 0; d < nd; ++d) {
+    int64_t oe = d < olead ? 1 : out->shape[d - olead];
+    o.shape[d] = oe;
+    o.strides[d] = d < olead ? 0 : out->strides[d - olead];
+    MDB_REQUIRE(oe == full[d] || oe == 1, "elementwise_reduce: output extent %lld does not match "
+                "iteration extent %lld on axis %d", (long long)oe, (long long)full[d], d);
+    redax[d] = (oe == 1 && full[d] != 1);
+  }
+  o.ndim = nd;
+  return reduce_driver(op, MDB_RED_SUM, &o, n_in, in, full, redax, nd, accumulate != 0);
+}
+
+}  // extern "C"

@@ -1,0 +1,246 @@
+// Runtime of libminidiff_b200: device/stream ownership, caching allocator, copies, events.
+// Stands behind array creation / as_numpy / finalizers of the backend boundary.
+#include <stdarg.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+#include <atomic>
+
+#include "mdb_common.cuh"
+
+namespace mdb {
+cudaStream_t g_stream = nullptr;
+int g_sm_count = 148;
+int g_device = -1;
+static thread_local char g_err[1024] = "";
+static std::atomic<uint64_t> g_launches{0};
+static std::mutex g_mu;
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+void count_launches(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int ensure_init() {
+  if (g_device >= 0) return 0;
+  return mdb_init(0);
+}
+
+// ---- caching allocator ---------------------------------------------------------------------
+// Blocks are rounded to a size class and kept on per-class free lists when released.  Reuse is
+// safe without events because every consumer runs on the single compute stream (stream order ==
+// program order); the comm stream only touches buffers between mdb_comm_allreduce_* and
+// mdb_comm_wait, during which the frontend keeps them alive.
+struct Allocator {
+  std::map<size_t, std::vector<void*>> free_lists;
+  std::unordered_map<void*, size_t> live;
+  size_t in_use = 0, cached = 0, peak = 0;
+  uint64_t n_device_allocs = 0;
+
+  static size_t round(size_t b) {
+    if (b == 0) b = 1;
+    if (b <= (1u << 20)) return (b + 511) & ~size_t(511);           // 512 B classes below 1 MiB
+    return (b + ((2u << 20) - 1)) & ~size_t((2u << 20) - 1);        // 2 MiB classes above
+  }
+  int alloc(size_t bytes, void** out) {
+    size_t r = round(bytes);
+    auto it = free_lists.find(r);
+    if (it != free_lists.end() && !it->second.empty()) {
+      *out = it->second.back();
+      it->second.pop_back();
+      cached -= r;
+    } else {
+      cudaError_t e = cudaMalloc(out, r);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        release_cached();
+        e = cudaMalloc(out, r);
+        if (e != cudaSuccess) {
+          cudaGetLastError();
+          return set_error(MDB_ENOMEM, "out of device memory allocating %zu bytes (%s)", r,
+                           cudaGetErrorString(e));
+        }
+      }
+      ++n_device_allocs;
+    }
+    live[*out] = r;
+    in_use += r;
+    if (in_use > peak) peak = in_use;
+    return 0;
+  }
+  int free(void* p) {
+    auto it = live.find(p);
+    if (it == live.end()) return set_error(MDB_EINVAL, "mdb_free: unknown pointer %p", p);
+    size_t r = it->second;
+    live.erase(it);
+    in_use -= r;
+    cached += r;
+    free_lists[r].push_back(p);
+    return 0;
+  }
+  void release_cached() {
+    if (g_stream) cudaStreamSynchronize(g_stream);
+    for (auto& kv : free_lists)
+      for (void* p : kv.second) cudaFree(p);
+    free_lists.clear();
+    cached = 0;
+  }
+};
+static Allocator g_alloc;
+}  // namespace mdb
+
+using namespace mdb;
+
+extern "C" {
+
+int mdb_abi_version(void) { return MDB_ABI_VERSION; }
+const char* mdb_last_error(void) { return g_err; }
+
+int mdb_device_count(int* count) {
+  cudaError_t e = cudaGetDeviceCount(count);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    *count = 0;
+    return set_error(MDB_ECUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+int mdb_init(int device) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_device >= 0) {
+    if (device != g_device)
+      return set_error(MDB_EINVAL, "already initialised on device %d (one backend per process)",
+                       g_device);
+    return 0;
+  }
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return set_error(MDB_ECUDA, "no CUDA device available (%s); minidiff_b200 has no CPU path",
+                     e == cudaSuccess ? "count is 0" : cudaGetErrorString(e));
+  }
+  MDB_REQUIRE(device >= 0 && device < n, "device %d out of range (have %d)", device, n);
+  MDB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  MDB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return set_error(MDB_ENOTSUP, "device %d is sm_%d%d; this library is built for sm_100a only",
+                     device, prop.major, prop.minor);
+  g_sm_count = prop.multiProcessorCount;
+  MDB_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  g_device = device;
+  return 0;
+}
+
+int mdb_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_device < 0) return 0;
+  g_alloc.release_cached();
+  cudaStreamDestroy(g_stream);
+  g_stream = nullptr;
+  g_device = -1;
+  return 0;
+}
+
+int mdb_device_info(int* sm_count, size_t* total_bytes, int* cc_major, int* cc_minor) {
+  MDB_TRY(ensure_init());
+  cudaDeviceProp prop;
+  MDB_CUDA(cudaGetDeviceProperties(&prop, g_device));
+  *sm_count = prop.multiProcessorCount;
+  *total_bytes = prop.totalGlobalMem;
+  *cc_major = prop.major;
+  *cc_minor = prop.minor;
+  return 0;
+}
+
+void* mdb_stream(void) { return (void*)g_stream; }
+
+int mdb_sync(void) {
+  MDB_TRY(ensure_init());
+  MDB_CUDA(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+
+int mdb_alloc(size_t bytes, void** out) {
+  MDB_TRY(ensure_init());
+  std::lock_guard<std::mutex> lk(g_mu);
+  return g_alloc.alloc(bytes, out);
+}
+int mdb_free(void* ptr) {
+  if (!ptr) return 0;
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_device < 0) return 0;  // after shutdown: memory already returned to the driver
+  return g_alloc.free(ptr);
+}
+int mdb_empty_cache(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_device >= 0) g_alloc.release_cached();
+  return 0;
+}
+int mdb_mem_stats(size_t* in_use, size_t* cached, size_t* peak, uint64_t* n_device_allocs) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  *in_use = g_alloc.in_use;
+  *cached = g_alloc.cached;
+  *peak = g_alloc.peak;
+  *n_device_allocs = g_alloc.n_device_allocs;
+  return 0;
+}
+int mdb_host_alloc(size_t bytes, void** out) {
+  MDB_TRY(ensure_init());
+  MDB_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return 0;
+}
+int mdb_host_free(void* ptr) {
+  if (ptr) MDB_CUDA(cudaFreeHost(ptr));
+  return 0;
+}
+
+int mdb_h2d(void* dst, const void* src, size_t bytes) {
+  MDB_TRY(ensure_init());
+  if (bytes) MDB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_stream));
+  return 0;
+}
+int mdb_d2h(void* dst, const void* src, size_t bytes) {
+  MDB_TRY(ensure_init());
+  if (bytes) MDB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_stream));
+  MDB_CUDA(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+int mdb_d2d(void* dst, const void* src, size_t bytes) {
+  MDB_TRY(ensure_init());
+  if (bytes) MDB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, g_stream));
+  return 0;
+}
+
+int mdb_event_create(void** ev) {
+  MDB_TRY(ensure_init());
+  cudaEvent_t e;
+  MDB_CUDA(cudaEventCreate(&e));
+  *ev = (void*)e;
+  return 0;
+}
+int mdb_event_record(void* ev) {
+  MDB_CUDA(cudaEventRecord((cudaEvent_t)ev, g_stream));
+  return 0;
+}
+int mdb_event_elapsed_ms(void* start, void* stop, float* ms) {
+  MDB_CUDA(cudaEventSynchronize((cudaEvent_t)stop));
+  MDB_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+  return 0;
+}
+int mdb_event_destroy(void* ev) {
+  MDB_CUDA(cudaEventDestroy((cudaEvent_t)ev));
+  return 0;
+}
+uint64_t mdb_launch_count(void) { return g_launches.load(); }
+
+}  // extern "C"

@@ -1,0 +1,404 @@
+"""Tensor: the user-facing value of the engine, holding device-resident storage.
+
+Public surface == the reference's `minidiff/tensor.py` (same class / attribute / function names and
+argument meaning, cited inline) so user code moves over by changing the import.  What differs is
+underneath: `_data` is a `DeviceArray` (device pointer + shape + strides), every property is answered
+from host-side metadata without touching the GPU, and operator overloads are generated from one
+table instead of being written out.
+"""
+from __future__ import annotations
+
+from contextvars import ContextVar
+
+import numpy as np
+
+import minidiff_b200.backend as backend
+
+DeviceArray = backend.DeviceArray
+
+# --------------------------------------------------------------------------- grad mode
+# reference tensor.py:19-69: two ContextVars, three context managers, four accessors
+_allow_grad = ContextVar("allow_grad", default=True)
+_allow_new_grads = ContextVar("allow_new_grads", default=True)
+
+
+def set_allow_grad(allow):
+    _allow_grad.set(allow)
+
+
+def grad_allowed_():
+    return _allow_grad.get()
+
+
+def set_allow_new_grads(allow):
+    _allow_new_grads.set(allow)
+
+
+def new_grads_allowed_():
+    return _allow_new_grads.get()
+
+
+class enable_grad:
+    """`with enable_grad(flag)`: graph recording on/off inside the block (tensor.py:44-53)."""
+
+    def __init__(self, enable):
+        self.enable = enable
+
+    def __enter__(self):
+        self._token = _allow_grad.set(self.enable)
+
+    def __exit__(self, *exc):
+        _allow_grad.reset(self._token)
+
+
+class no_grad(enable_grad):
+    """tensor.py:35-41"""
+
+    def __init__(self):
+        super().__init__(False)
+
+
+class disable_new_grads:
+    """tensor.py:23-32"""
+
+    def __enter__(self):
+        self._tokens = (_allow_grad.set(False), _allow_new_grads.set(False))
+
+    def __exit__(self, *exc):
+        _allow_grad.reset(self._tokens[0])
+        _allow_new_grads.reset(self._tokens[1])
+
+
+def try_unwrap(t):
+    """Tensor -> raw device array, recursively through tuple/list/dict (tensor.py:72-82)."""
+    if isinstance(t, Tensor):
+        return t._data
+    if isinstance(t, tuple):
+        return tuple(try_unwrap(x) for x in t)
+    if isinstance(t, list):
+        return [try_unwrap(x) for x in t]
+    if isinstance(t, dict):
+        return {k: try_unwrap(v) for k, v in t.items()}
+    return t
+
+
+class Tensor:
+    """reference tensor.py:92-433"""
+
+    __slots__ = ("_data", "_allow_grad", "_iterator", "graph_refs", "grad", "op_node",
+                 "_grad_private", "__weakref__")
+    __array_ufunc__ = None  # numpy scalars defer to our reflected operators
+
+    def __init__(self, data, allow_grad=False, dtype=None):
+        data = try_unwrap(data)
+        if data is None:
+            data = backend.tensor_constructor([])
+        if not isinstance(data, DeviceArray):
+            data = backend.tensor_constructor(data)
+        if dtype is not None:
+            data = data.astype(dtype)
+        self._data = data
+        self._allow_grad = allow_grad
+        self._iterator = None
+        self.graph_refs = 0
+        self.grad = None
+        self.op_node = None
+        # the grad Tensor whose buffer this tensor exclusively owns during the current backward
+        # sweep (may be accumulated into in place); see topology.OpNode.accumulate
+        self._grad_private = None
+
+    # ---- graph flags (tensor.py:115-148)
+    @property
+    def graphed(self):
+        return self.graph_refs > 0 or self.op_node is not None
+
+    @property
+    def is_leaf(self):
+        return self.op_node is None
+
+    @property
+    def allow_grad(self):
+        return self._allow_grad
+
+    @allow_grad.setter
+    def allow_grad(self, allow_grad):
+        if not allow_grad and self.op_node is not None:
+            raise ValueError("Turning off gradient tracking for intermediate tensors will almost "
+                             "always break chain rule in backprop")
+        if self._allow_grad != allow_grad:
+            self.grad = None
+            self._allow_grad = allow_grad
+
+    # ---- metadata: host-side only, never a device sync (tensor.py:150-171)
+    T = property(lambda self: md.transpose(self))
+    shape = property(lambda self: self._data.shape)
+    size = property(lambda self: self._data.size)
+    ndim = property(lambda self: len(self._data.shape))
+    dtype = property(lambda self: self._data.dtype)
+
+    def as_numpy(self):
+        return backend.as_numpy(self._data)
+
+    # ---- autodiff entry (tensor.py:173-203)
+    def backward(self, retain_grads=False, cleanup_mode="prune", allow_higher_order=False,
+                 reset_grads=True):
+        if not self._allow_grad or self.op_node is None:
+            return
+        self.grad = ones_like(self, allow_grad=allow_higher_order)
+        self.op_node.backward(self.grad, retain_grads=retain_grads, cleanup_mode=cleanup_mode,
+                              allow_higher_order=allow_higher_order, reset_grads=reset_grads)
+
+    def wipe(self):
+        self.op_node = None
+
+    def detach(self, allow_grad=False):
+        return Tensor(self._data, allow_grad=allow_grad)  # shares storage
+
+    # ---- method sugar (tensor.py:205-255)
+    def ravel(self, order="C"): return md.ravel(self, order=order)
+    def flatten(self, order="C"): return md.flatten(self, order=order)
+    def astype(self, dtype): return md.astype(self, dtype)
+    def transpose(self, axes=None): return md.transpose(self, axes=axes)
+    def sum(self, axis=None, keepdims=False): return md.sum(self, axis=axis, keepdims=keepdims)
+    def copy(self): return md.copy(self)
+    def clip(self, a_min=None, a_max=None): return md.clip(self, a_min=a_min, a_max=a_max)
+    def reshape(self, shape): return md.reshape(self, shape)
+    def dot(self, other): return md.dot(self, other)
+    def matmul(self, other): return md.matmul(self, other)
+    def add(self, other): return md.add(self, other)
+    def multiply(self, other): return md.multiply(self, other)
+
+    def item(self):
+        if self.size != 1:
+            raise ValueError("Only Tensors with a single element can be reduced to a Python scalar")
+        return backend.tensor_item(self._data)
+
+    # ---- in-place mutation guard (tensor.py:257-264)
+    def _graph_tracking(self):
+        return self._allow_grad and grad_allowed_() and self.graphed
+
+    def _validate_mutation(self):
+        if self._graph_tracking():
+            raise ValueError("In-place operations can break computation graphs during backprop")
+
+    def __neg__(self):
+        return -1 * self
+
+    def __repr__(self):
+        return backend.repr(self._data)
+
+    def __len__(self):
+        return backend.len(self._data)
+
+    def __getitem__(self, key):
+        return md.getitem(self, key)
+
+    def __setitem__(self, key, val):
+        self._validate_mutation()
+        self._data[try_unwrap(key)] = try_unwrap(val)
+
+    def __imatmul__(self, other):
+        self._validate_mutation()
+        self._data @= other._data
+        return self
+
+    def __invert__(self):
+        return md.invert(self)
+
+    def __not__(self, value):
+        return md.logical_not(self, value)
+
+    __hash__ = None  # __eq__ is elementwise (tensor.py:393)
+
+    def __iter__(self):
+        if self._iterator is None:
+            n = self._data.size
+            self._iterator = TensorIterator(self, len(self) if n > 1 else n)
+        return self._iterator
+
+    # ---- NumPy interop (tensor.py:423-433): no host interface, only an explicit copy
+    @property
+    def __array_interface__(self):
+        return backend.array_interface(self._data)
+
+    def __array__(self, dtype=None, copy=None):
+        return backend.array(self._data, dtype=dtype, copy=copy)
+
+
+def _install_operators():
+    """Operator overloads route to ops; augmented assignments mutate storage directly with one
+    in-place kernel (reference tensor.py:266-412)."""
+    binary = {"add": "add", "sub": "subtract", "mul": "multiply", "truediv": "true_divide",
+              "floordiv": "floor_divide", "pow": "power", "mod": "mod", "matmul": "matmul"}
+    for dunder, op in binary.items():
+        def fwd(self, other, _op=op):
+            return getattr(md, _op)(self, other)
+
+        def rev(self, other, _op=op):
+            return getattr(md, _op)(other, self)
+
+        setattr(Tensor, f"__{dunder}__", fwd)
+        if dunder not in ("mod", "matmul"):
+            setattr(Tensor, f"__r{dunder}__", rev)
+    compare = {"gt": "greater", "ge": "greater_equal", "lt": "less", "le": "less_equal",
+               "eq": "equal", "ne": "not_equal", "and": "logical_and", "or": "logical_or",
+               "xor": "logical_xor"}
+    for dunder, op in compare.items():
+        def cmp(self, value, _op=op):
+            return getattr(md, _op)(self, value)
+
+        setattr(Tensor, f"__{dunder}__", cmp)
+    for dunder in ("iadd", "isub", "imul", "itruediv", "ifloordiv", "ipow", "imod"):
+        def inplace(self, other, _d=f"__{dunder}__"):
+            self._validate_mutation()
+            getattr(self._data, _d)(try_unwrap(other))
+            return self
+
+        setattr(Tensor, f"__{dunder}__", inplace)
+
+
+class TensorIterator:
+    """tensor.py:436-450 (cached on the tensor and single-use, like the reference's)"""
+
+    def __init__(self, data, length):
+        self.data, self.length, self.index = data, length, 0
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self.index >= self.length:
+            raise StopIteration
+        item = self.data[self.index]
+        self.index += 1
+        return item
+
+
+# --------------------------------------------------------------------------- creation helpers
+# (reference tensor.py:453-677; non-differentiable, results enter the graph as leaves)
+def _leaf(raw, allow_grad=False):
+    return Tensor(raw, allow_grad=allow_grad)
+
+
+def ones_like(a, allow_grad=False): return _leaf(backend.ones_like(try_unwrap(a)), allow_grad)
+def ones(shape, allow_grad=False): return _leaf(backend.ones(shape), allow_grad)
+def zeros_like(a, allow_grad=False): return _leaf(backend.zeros_like(try_unwrap(a)), allow_grad)
+def zeros(shape, allow_grad=False): return _leaf(backend.zeros(shape), allow_grad)
+
+
+def full_like(a, x, allow_grad=False):
+    return _leaf(backend.full_like(try_unwrap(a), try_unwrap(x)), allow_grad)
+
+
+def full(shape, fill_value=None, allow_grad=False):
+    # the reference drops the fill value (tensor.py:480-481, SURVEY App. C #16: unusable as
+    # written); accepting it as the second argument keeps every working call working
+    if fill_value is None:
+        raise TypeError("full() missing required argument 'fill_value'")
+    return _leaf(backend.full(shape, try_unwrap(fill_value)), allow_grad)
+
+
+def concatenate(arrays, axis=0, allow_grad=False):
+    return _leaf(backend.concatenate(try_unwrap(arrays), axis=axis), allow_grad)
+
+
+def index_add(a, indices, b=None):
+    backend.index_add(try_unwrap(a), try_unwrap(indices), try_unwrap(b))
+
+
+def isin(element, test_elements):
+    return backend.isin(try_unwrap(element), try_unwrap(test_elements))
+
+
+def unravel_index(indices, shape, allow_grad=False):
+    return _leaf(backend.unravel_index(try_unwrap(indices), shape), allow_grad)
+
+
+def vmap(fun):
+    """tensor.py:518-536"""
+
+    def on_raw(arr, *args, **kwargs):
+        args = [Tensor(x) for x in args]
+        kwargs = {k: Tensor(v) for k, v in kwargs.items()}
+        return fun(Tensor(arr), *args, **kwargs)._data
+
+    mapped = backend.vmap(on_raw)
+
+    def wrapper(*args, **kwargs):
+        return Tensor(mapped(*try_unwrap(args), **try_unwrap(kwargs)))
+
+    return wrapper
+
+
+def take_along_axis(arr, indices, axis=None, allow_grad=False):
+    return _leaf(backend.take_along_axis(arr._data, indices._data, axis=axis), allow_grad)
+
+
+def put_along_axis(arr, indices, values, axis):
+    backend.put_along_axis(arr._data, indices._data, try_unwrap(values), axis)
+
+
+def repeat(a, repeats, allow_grad=False, axis=None):
+    return _leaf(backend.repeat(try_unwrap(a), repeats, axis=axis), allow_grad)
+
+
+def tile(A, reps, allow_grad=False):
+    return _leaf(backend.tile(try_unwrap(A), try_unwrap(reps)), allow_grad)
+
+
+def arange(*args, allow_grad=False):
+    return _leaf(backend.arange(*args), allow_grad)
+
+
+def stack(arrays, axis=0, allow_grad=False):
+    return _leaf(backend.stack([x._data for x in arrays], axis=axis), allow_grad)
+
+
+def save(file, arr):
+    backend.save(file, arr._data)
+
+
+def load(file, allow_grad=False):
+    return _leaf(backend.load(file), allow_grad)
+
+
+def choice(a, size=None, replace=True, p=None):
+    return Tensor(backend.choice(try_unwrap(a), size=size, replace=replace, p=try_unwrap(p)))
+
+
+def rand(*dims, allow_grad=False): return _leaf(backend.rand(*dims), allow_grad)
+def randn(*dims, allow_grad=False): return _leaf(backend.randn(*dims), allow_grad)
+
+
+def randint(low, high=None, size=None, allow_grad=False):
+    return _leaf(backend.randint(try_unwrap(low), high=try_unwrap(high), size=size), allow_grad)
+
+
+def binomial(n, p, size=None, allow_grad=False):
+    return _leaf(backend.binomial(try_unwrap(n), try_unwrap(p), size=size), allow_grad)
+
+
+def permutation(x, allow_grad=False):
+    return _leaf(backend.permutation(try_unwrap(x)), allow_grad)
+
+
+def shuffle(x):
+    backend.shuffle(x._data)
+
+
+def split(ary, indices_or_sections, axis=0, allow_grad=False):
+    parts = backend.split(ary._data, try_unwrap(indices_or_sections), axis=axis)
+    return [Tensor(p, allow_grad=allow_grad) for p in parts]
+
+
+dtypes = [
+    float64 := backend.float64, float32 := backend.float32, float16 := backend.float16,
+    uint64 := backend.uint64, uint32 := backend.uint32, uint16 := backend.uint16,
+    uint8 := backend.uint8, int64 := backend.int64, int32 := backend.int32,
+    int16 := backend.int16, int8 := backend.int8, bool := backend.bool,
+]
+newaxis = None
+
+import minidiff_b200 as md  # noqa: E402  (ops are resolved lazily through the package, like the reference)
+
+_install_operators()

@@ -1,0 +1,393 @@
+"""GPU parity of the backend function table (C ABI -> CUDA kernels) against NumPy, which IS the
+reference implementation of every backend function (reference backend/numpy.py binds np.<name>).
+Tolerances are the north_star's: exact for shapes / indexing / integer & bool results, <= 2 ulp for
+fp32 elementwise, rtol 1e-4 / atol 1e-5 for reductions and GEMMs."""
+import numpy as np
+import pytest
+
+from conftest import ulp_diff
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def B():
+    import minidiff_b200.backend as backend
+
+    backend.assert_live()
+    return backend
+
+
+def dev(B, x):
+    return B.asarray(x) if isinstance(x, np.ndarray) else x
+
+
+def host(r):
+    return r.numpy() if hasattr(r, "numpy") else np.asarray(r)
+
+
+def same_meta(got, want):
+    want = np.asarray(want)
+    assert tuple(got.shape) == want.shape, (got.shape, want.shape)
+    assert got.dtype == want.dtype, (got.dtype, want.dtype)
+
+
+def check(got, want, ulp=0, rtol=None, atol=0.0):
+    same_meta(got, want)
+    g, w = host(got), np.asarray(want)
+    if rtol is not None:
+        np.testing.assert_allclose(g, w, rtol=rtol, atol=atol, equal_nan=True)
+    elif w.dtype == np.float32 and ulp:
+        assert np.array_equal(np.isnan(g), np.isnan(w))
+        d = ulp_diff(np.nan_to_num(g), np.nan_to_num(w))
+        assert d.max(initial=0) <= ulp, f"max ulp {d.max()}"
+    else:
+        np.testing.assert_array_equal(g, w)
+
+
+RNG = np.random.default_rng(42)
+
+
+def f32(*shape, scale=1.0):
+    return (RNG.standard_normal(shape) * scale).astype(np.float32)
+
+
+SHAPES_BIN = [((5, 7), (5, 7)), ((5, 1), (1, 7)), ((5, 7), (7,)), ((1,), (3, 4, 5)),
+              ((4, 1, 6), (3, 1)), ((1024, 1), (1, 1024)), ((333, 127), (333, 127)),
+              ((64, 1024), (1024,)), ((2, 3, 4, 5, 6), (5, 1)), ((), (3, 3))]
+
+
+@pytest.mark.parametrize("name", ["add", "subtract", "multiply", "true_divide"])
+@pytest.mark.parametrize("sa,sb", SHAPES_BIN)
+def test_binary_arith_exact(B, name, sa, sb):
+    a, b = f32(*sa), f32(*sb)
+    check(getattr(B, name)(dev(B, a), dev(B, b)), getattr(np, name)(a, b))
+
+
+@pytest.mark.parametrize("name", ["add", "subtract", "multiply", "true_divide", "power", "mod",
+                                  "floor_divide", "greater", "less_equal", "equal"])
+@pytest.mark.parametrize("scalar", [2, 2.5, -1, 0, 0.5])
+def test_binary_python_scalar_is_weak(B, name, scalar):
+    a = np.abs(f32(6, 9)) + 0.25
+    if name in ("mod", "floor_divide", "true_divide") and scalar == 0:
+        pytest.skip("division by zero warnings differ only in warnings")
+    ulp = 2 if name == "power" else 0
+    check(getattr(B, name)(dev(B, a), scalar), getattr(np, name)(a, scalar), ulp=ulp)
+    if name != "power" or scalar > 0:
+        check(getattr(B, name)(scalar, dev(B, a)), getattr(np, name)(scalar, a), ulp=ulp)
+
+
+@pytest.mark.parametrize("name,ulp", [("sin", 2), ("cos", 2), ("exp", 2), ("tan", 2), ("sinh", 2),
+                                      ("cosh", 2), ("tanh", 2), ("absolute", 0), ("sign", 0),
+                                      ("ceil", 0), ("floor", 0)])
+def test_unary_fp32(B, name, ulp):
+    a = f32(257, 33, scale=3.0)
+    check(getattr(B, name)(dev(B, a)), getattr(np, name)(a), ulp=ulp)
+
+
+def test_unary_fp32_vs_float64_truth(B):
+    """Device error against the correctly rounded result (the budget is 2 ulp; NumPy's own SIMD
+    paths are 1-3 ulp from truth, SURVEY finding 5, so this is the stricter, host-independent check)."""
+    a = f32(1 << 16, scale=4.0)
+    for name in ("sin", "cos", "exp", "tanh"):
+        truth = getattr(np, name)(a.astype(np.float64)).astype(np.float32)
+        d = ulp_diff(host(getattr(B, name)(dev(B, a))), truth)
+        assert d.max() <= 2, (name, d.max())
+    p = np.abs(a) + 1e-3
+    assert ulp_diff(host(B.log(dev(B, p))), np.log(p.astype(np.float64)).astype(np.float32)).max() <= 2
+    assert ulp_diff(host(B.power(dev(B, p), 2.5)),
+                    np.power(p.astype(np.float64), 2.5).astype(np.float32)).max() <= 2
+
+
+def test_log_sqrt_power_fastpaths(B):
+    p = np.abs(f32(100, 40)) + 0.1
+    check(B.log(dev(B, p)), np.log(p), ulp=2)
+    for e in (2, 1, 0, 0.5, -1):   # NumPy's exact scalar-exponent forms (SURVEY finding 5)
+        check(B.power(dev(B, p), e), np.power(p, e))
+    for e in (3, 2.5, -0.5):
+        check(B.power(dev(B, p), e), np.power(p, e), ulp=2)
+    e = np.abs(f32(100, 40)) + 0.5
+    check(B.power(dev(B, p), dev(B, e)), np.power(p, e), ulp=2)
+
+
+@pytest.mark.parametrize("name", ["greater", "greater_equal", "less", "less_equal", "equal",
+                                  "not_equal", "logical_and", "logical_or", "logical_xor"])
+def test_predicates(B, name):
+    a, b = f32(33, 65), f32(33, 65)
+    b[::3] = a[::3]
+    check(getattr(B, name)(dev(B, a), dev(B, b)), getattr(np, name)(a, b))
+    check(getattr(B, name)(dev(B, a), 0), getattr(np, name)(a, 0))
+
+
+def test_where_clip_mask(B):
+    a, b = f32(128, 96), f32(128, 96)
+    m = a > 0
+    check(B.where(dev(B, m), dev(B, a), 0), np.where(m, a, 0))
+    check(B.where(dev(B, m), dev(B, a), dev(B, b)), np.where(m, a, b))
+    check(B.where(dev(B, a > b), 1.5, dev(B, b)), np.where(a > b, 1.5, b))
+    check(B.clip(dev(B, a), 0, None), np.clip(a, 0, None))
+    check(B.clip(dev(B, a), -0.5, 0.5), np.clip(a, -0.5, 0.5))
+    check(B.multiply(dev(B, a), dev(B, m)), np.multiply(a, m))           # f32 * bool mask (C4 bwd)
+    check(B.subtract(1, dev(B, m)), np.subtract(1, m))                   # 1 - condition -> int64
+    check(B.multiply(dev(B, a), B.subtract(1, dev(B, m))), a * (1 - m))  # -> float64 (SURVEY C#13)
+    check(B.logical_not(dev(B, m)), np.logical_not(m))
+    check(B.invert(dev(B, m)), np.invert(m))
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.int64, np.int32, np.bool_, np.uint8, np.int16])
+def test_dtype_promotion_matches_numpy(B, dt):
+    a = (RNG.standard_normal((9, 11)) * 5).astype(dt)
+    b = f32(9, 11)
+    for name in ("add", "multiply", "subtract", "true_divide", "greater"):
+        want = getattr(np, name)(a, b)
+        check(getattr(B, name)(dev(B, a), dev(B, b)), want,
+              rtol=1e-6 if want.dtype.kind == "f" else None)
+        want = getattr(np, name)(a, a)
+        if name == "true_divide":
+            continue
+        if dt == np.bool_ and name == "subtract":
+            continue  # NumPy raises for bool - bool
+        check(getattr(B, name)(dev(B, a), dev(B, a)), want, rtol=1e-12 if want.dtype.kind == "f" else None)
+    check(B.sin(dev(B, a)).astype(np.float64), np.sin(a).astype(np.float64), rtol=1e-3, atol=1e-3)
+    check(B.add(dev(B, a), 2.5), np.add(a, 2.5), rtol=1e-12)
+    check(B.astype(dev(B, b), dt), b.astype(dt))
+
+
+def test_strided_and_broadcast_views_as_operands(B):
+    a = f32(64, 48)
+    da = dev(B, a)
+    check(B.add(da.T, dev(B, a.T.copy())), a.T + a.T)                       # F-order view operand
+    check(B.multiply(da[::2, 1::3], 2.0), a[::2, 1::3] * 2.0)               # strided slice
+    check(B.add(B.broadcast_to(da[0], (64, 48)), da), np.broadcast_to(a[0], (64, 48)) + a)
+    check(B.flip(da, axis=1), np.flip(a, axis=1))
+    check(B.sin(B.flip(da)), np.sin(np.flip(a)), ulp=2)
+    s0 = B.broadcast_to(B.asarray(np.float32(3.0)), (17, 19))               # stride-0 everywhere
+    assert s0.strides == (0, 0)
+    check(B.multiply(s0, 2), np.full((17, 19), 6.0, np.float32))
+
+
+def test_inplace_family_and_readonly(B):
+    a, b = f32(40, 24), f32(40, 24)
+    da = dev(B, a.copy())
+    da += dev(B, b); a += b
+    da -= 0.5 * 1; a -= 0.5
+    da *= dev(B, b[0]); a *= b[0]
+    da /= 3; a /= 3
+    da **= 2; a **= 2
+    check(da, a)
+    ro = B.broadcast_to(dev(B, f32(24)), (40, 24))
+    with pytest.raises(ValueError):
+        ro += 1.0
+    with pytest.raises(ValueError):
+        da += dev(B, f32(41, 24))
+    ia = dev(B, np.arange(6))
+    with pytest.raises(TypeError):
+        ia += 0.5
+    m = dev(B, f32(8, 8)); m2 = host(m).copy()
+    m @= dev(B, np.eye(8, dtype=np.float32))
+    check(m, m2, rtol=1e-6)
+
+
+RED_SHAPES = [((7,), None), ((5, 7), None), ((5, 7), (0,)), ((5, 7), (1,)), ((5, 7), 1),
+              ((3, 4, 5), (0, 2)), ((3, 4, 5), (1,)), ((3, 4, 5), (0, 1)), ((3, 4, 5), (1, 2)),
+              ((1000, 3), (0,)), ((3, 5000), (1,)), ((2048, 2048), (0,)), ((2048, 2048), (1,)),
+              ((2048, 2048), None), ((1 << 20,), None), ((300, 1, 17), (0,)), ((17, 4097), (1,)),
+              ((4097, 17), (0,)), ((64, 33, 65), (1,)), ((2, 3, 4, 5), (1, 3))]
+
+
+@pytest.mark.parametrize("shape,axis", RED_SHAPES)
+@pytest.mark.parametrize("keepdims", [False, True])
+def test_sum_mean(B, shape, axis, keepdims):
+    a = f32(*shape)
+    for name in ("sum", "mean"):
+        got = getattr(B, name)(dev(B, a), axis=axis, keepdims=keepdims)
+        want = getattr(np, name)(a, axis=axis, keepdims=keepdims)
+        truth = getattr(np, name)(a.astype(np.float64), axis=axis, keepdims=keepdims)
+        same_meta(got, want)
+        # device vs float64 truth must be at least as tight as the budget; NumPy's own column
+        # sums are naive and can be further from truth than we are (SURVEY hard parts)
+        scale = np.abs(a).astype(np.float64).sum(axis=axis, keepdims=keepdims) if name == "sum" else \
+            np.abs(a).astype(np.float64).mean(axis=axis, keepdims=keepdims)
+        err = np.abs(host(got).astype(np.float64) - truth)
+        assert np.all(err <= 1e-5 + 1e-4 * np.abs(truth) + 2e-7 * scale), err.max()
+
+
+@pytest.mark.parametrize("shape,axis", RED_SHAPES[:12])
+def test_max_min_any_all_prod_arg(B, shape, axis):
+    a = f32(*shape)
+    check(B.max(dev(B, a), axis=axis), np.max(a, axis=axis))
+    check(B.min(dev(B, a), axis=axis, keepdims=True), np.min(a, axis=axis, keepdims=True))
+    check(B.any(dev(B, a > 1), axis=axis), np.any(a > 1, axis=axis))
+    check(B.all(dev(B, a > -3), axis=axis), np.all(a > -3, axis=axis))
+    small = (a * 0.1 + 1).astype(np.float32)
+    check(B.prod(dev(B, small), axis=axis), np.prod(small, axis=axis), rtol=1e-4, atol=1e-30)
+    if axis is None or isinstance(axis, int) or len(axis) == 1:
+        ax = axis if axis is None or isinstance(axis, int) else axis[0]
+        check(B.argmax(dev(B, a), axis=ax), np.argmax(a, axis=ax))
+        check(B.argmin(dev(B, a), axis=ax, keepdims=True), np.argmin(a, axis=ax, keepdims=True))
+
+
+def test_reductions_on_views_and_ints(B):
+    a = f32(96, 80)
+    da = dev(B, a)
+    check(B.sum(da.T, axis=0), np.sum(a.T, axis=0), rtol=1e-5, atol=1e-5)
+    check(B.sum(da[::2, ::3], axis=1), np.sum(a[::2, ::3], axis=1), rtol=1e-5, atol=1e-5)
+    check(B.sum(B.broadcast_to(da[0], (10, 80)), axis=0), np.sum(np.broadcast_to(a[0], (10, 80)), axis=0),
+          rtol=1e-5, atol=1e-5)
+    i = RNG.integers(-5, 5, (13, 7))
+    check(B.sum(dev(B, i), axis=0), np.sum(i, axis=0))
+    check(B.sum(dev(B, i > 0)), np.sum(i > 0))
+    check(B.mean(dev(B, i), axis=1), np.mean(i, axis=1), rtol=1e-12)
+    check(B.std(da, axis=(1,)), np.std(a, axis=(1,)), rtol=1e-4, atol=1e-6)
+    check(B.std(da), np.std(a), rtol=1e-4, atol=1e-6)
+    with pytest.raises(np.exceptions.AxisError):
+        B.sum(da, axis=2)
+
+
+GEMM_SHAPES = [(10, 30, 20), (1, 1, 1), (64, 64, 64), (48, 40, 56), (128, 256, 128), (257, 129, 65),
+               (512, 384, 256), (1024, 1024, 1024)]
+
+
+@pytest.mark.parametrize("M,K,N", GEMM_SHAPES)
+def test_matmul_all_layouts(B, M, K, N):
+    a, b = f32(M, K), f32(K, N)
+    want = a.astype(np.float64) @ b.astype(np.float64)
+    tol = dict(rtol=1e-4, atol=1e-5 * np.sqrt(K))
+    check(B.matmul(dev(B, a), dev(B, b)), (a @ b), **tol)                           # NN
+    np.testing.assert_allclose(host(B.matmul(dev(B, a), dev(B, b))), want, **tol)
+    bt = dev(B, np.ascontiguousarray(b.T))
+    check(B.matmul(dev(B, a), bt.T), a @ b, **tol)                                   # NT (dA form)
+    at = dev(B, np.ascontiguousarray(a.T))
+    check(B.matmul(at.T, dev(B, b)), a @ b, **tol)                                   # TN (dB form)
+    check(B.matmul(at.T, bt.T), a @ b, **tol)                                        # TT
+
+
+def test_matmul_misc(B):
+    a, b = f32(6, 5), f32(5, 4)
+    with pytest.raises(ValueError):
+        B.matmul(dev(B, a), dev(B, a))
+    check(B.matmul(dev(B, a), dev(B, b[:, 0])), a @ b[:, 0], rtol=1e-5, atol=1e-6)
+    check(B.matmul(dev(B, a[0]), dev(B, b)), a[0] @ b, rtol=1e-5, atol=1e-6)
+    x, y = f32(3, 2, 6, 5), f32(2, 5, 4)
+    check(B.matmul(dev(B, x), dev(B, y)), x @ y, rtol=1e-5, atol=1e-6)
+    a64, b64 = a.astype(np.float64), b.astype(np.float64)
+    check(B.matmul(dev(B, a64), dev(B, b64)), a64 @ b64, rtol=1e-12)
+    p, q = f32(3, 4, 5), f32(4, 5, 6)
+    check(B.tensordot(dev(B, p), dev(B, q), axes=2), np.tensordot(p, q, axes=2), rtol=1e-5, atol=1e-5)
+    check(B.tensordot(dev(B, p), dev(B, q), axes=((1,), (0,))), np.tensordot(p, q, axes=((1,), (0,))),
+          rtol=1e-5, atol=1e-5)
+    v, w = f32(9), f32(9)
+    check(B.dot(dev(B, v), dev(B, w)), np.dot(v, w), rtol=1e-5, atol=1e-6)
+
+
+def test_view_functions_exact(B):
+    a = f32(3, 1, 4, 5)
+    da = dev(B, a)
+    for fn, args, kw in [("transpose", (), {}), ("transpose", ((2, 0, 3, 1),), {}),
+                         ("swapaxes", (0, 2), {}), ("squeeze", (), {}), ("squeeze", (), {"axis": 1}),
+                         ("expand_dims", (2,), {}), ("expand_dims", ((0, 3),), {}),
+                         ("reshape", ((12, 5),), {}), ("reshape", ((-1,),), {}),
+                         ("reshape", ((5, 12),), {"order": "F"}), ("ravel", (), {}),
+                         ("ravel", (), {"order": "F"}), ("flatten", (), {}), ("flip", (), {"axis": 2}),
+                         ("broadcast_to", ((2, 3, 3, 4, 5),), {}), ("atleast_3d", (), {}),
+                         ("copy", (), {})]:
+        check(getattr(B, fn)(da, *args, **kw), getattr(np, fn)(a, *args, **kw))
+    assert B.transpose(da).strides == np.transpose(a).strides
+    assert B.reshape(B.transpose(da[:, 0]), (20, 3)).shape == (20, 3)       # copy path
+    check(B.reshape(B.transpose(da[:, 0]), (20, 3)), np.reshape(np.transpose(a[:, 0]), (20, 3)))
+    check(B.atleast_1d(dev(B, np.float32(2))), np.atleast_1d(np.float32(2)))
+    check(B.atleast_2d(dev(B, a[0, 0, 0])), np.atleast_2d(a[0, 0, 0]))
+    with pytest.raises(ValueError):
+        B.reshape(da, (7, 9))
+    with pytest.raises(ValueError):
+        B.broadcast_to(da, (3, 2, 4, 5))
+
+
+def test_indexing(B):
+    a = f32(6, 7, 8)
+    da = dev(B, a)
+    for key in [2, (1, 2), (slice(1, 5), slice(None, None, 2)), (Ellipsis, 3), (None, 1, None),
+                (slice(None), -1), (slice(4, 1, -1),), (1, Ellipsis, slice(2, 6))]:
+        check(da[key], a[key])
+    idx = np.array([5, 0, 0, -1, 3])
+    check(da[dev(B, idx)], a[idx])
+    check(da[dev(B, idx), dev(B, np.array([1, 2, 3, 4, 6]))], a[idx, np.array([1, 2, 3, 4, 6])])
+    check(da[dev(B, a[:, 0, 0] > 0)], a[a[:, 0, 0] > 0])
+    with pytest.raises(IndexError):
+        da[6]
+    b = a.copy(); db = dev(B, b)
+    db[1:3, ::2] = 7.0; b[1:3, ::2] = 7.0
+    db[0] = dev(B, a[1]); b[0] = a[1]
+    db[dev(B, idx)] = 1.5; b[idx] = 1.5
+    check(db, b)
+    c = np.zeros((6, 7), np.float32); dc = dev(B, c)
+    B.index_add(dc, dev(B, idx), dev(B, a[:5, :, 0])); np.add.at(c, idx, a[:5, :, 0])
+    B.index_add(dc, (slice(1, 3),), 2.0); np.add.at(c, (slice(1, 3),), 2.0)
+    check(dc, c, rtol=1e-6)
+    ii = RNG.integers(0, 7, (6, 1, 8))
+    check(B.take_along_axis(da, dev(B, ii), axis=1), np.take_along_axis(a, ii, axis=1))
+    z = np.zeros_like(a); dz = dev(B, z)
+    B.put_along_axis(dz, dev(B, ii), dev(B, a[:, :1, :]), 1); np.put_along_axis(z, ii, a[:, :1, :], 1)
+    check(dz, z)
+
+
+def test_creation_and_layout_helpers(B):
+    a, b = f32(3, 4), f32(3, 4)
+    check(B.ones((2, 3)), np.ones((2, 3)))
+    check(B.zeros(4), np.zeros(4))
+    check(B.full((2, 2), 3), np.full((2, 2), 3))
+    check(B.ones_like(dev(B, a)), np.ones_like(a))
+    check(B.zeros_like(dev(B, a)), np.zeros_like(a))
+    check(B.full_like(dev(B, a), 2.5), np.full_like(a, 2.5))
+    check(B.arange(2, 11, 3), np.arange(2, 11, 3))
+    check(B.concatenate([dev(B, a), dev(B, b)], axis=1), np.concatenate([a, b], axis=1))
+    check(B.stack([dev(B, a), dev(B, b)], axis=0), np.stack([a, b], axis=0))
+    for got, want in zip(B.split(dev(B, a), 2, axis=1), np.split(a, 2, axis=1)):
+        check(got, want)
+    check(B.tile(dev(B, a), (2, 1, 3)), np.tile(a, (2, 1, 3)))
+    check(B.tile(dev(B, a), (5, 1, 1)), np.tile(a, (5, 1, 1)))
+    check(B.repeat(dev(B, a), 3, axis=0), np.repeat(a, 3, axis=0))
+    check(B.tensor_constructor([[1, 2], [3, 4]]), np.array([[1, 2], [3, 4]]))
+    check(B.tensor_constructor([]), np.array([]))
+    check(B.tensor_constructor(2.5), np.array(2.5))
+    assert B.tensor_item(B.sum(dev(B, np.ones((3, 3), np.float32)))) == 9.0
+    assert B.tensor_shape(dev(B, a)) == (3, 4) and B.tensor_size(dev(B, a)) == 12
+    assert B.len(dev(B, a)) == 3 and "array" in B.repr(dev(B, a))
+    np.testing.assert_array_equal(np.asarray(dev(B, a)), a)                  # __array__ protocol
+    with pytest.raises(AttributeError):
+        B.array_interface(dev(B, a))
+    r = B.vmap(lambda row: B.sum(row))(dev(B, a))
+    check(r, a.sum(axis=1), rtol=1e-6)
+
+
+def test_random_helpers_distribution(B):
+    B.seed(7)
+    r = host(B.randn(1 << 16))
+    assert r.dtype == np.float64 and abs(r.mean()) < 0.02 and abs(r.std() - 1) < 0.02
+    u = host(B.rand(1 << 16))
+    assert 0 <= u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 0.01
+    k = host(B.randint(2, 9, size=(1000,)))
+    assert k.min() >= 2 and k.max() <= 8
+    p = host(B.permutation(50))
+    assert sorted(p.tolist()) == list(range(50))
+    assert host(B.binomial(10, 0.5, size=(2000,))).mean() == pytest.approx(5, abs=0.3)
+    assert host(B.choice(10, size=(7,))).shape == (7,)
+
+
+def test_allocator_reuses_blocks(B):
+    import ctypes as C
+
+    from minidiff_b200.backend._lib import lib
+
+    def stats():
+        v = [C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_uint64()]
+        lib.mdb_mem_stats(*[C.byref(x) for x in v])
+        return [x.value for x in v]
+
+    x = B.ones((1 << 20,), dtype=np.float32)
+    del x
+    n0 = stats()[3]
+    for _ in range(20):
+        y = B.ones((1 << 20,), dtype=np.float32)
+        del y
+    assert stats()[3] == n0, "freed blocks must be served from the cache, not cudaMalloc"

@@ -1,0 +1,442 @@
+"""GPU parity of the engine (Tensor / ops / OpNode on device storage) against (a) golden vectors
+produced by the REAL reference (tests/golden) and (b) the pinned NumPy oracle on seeded inputs at
+sizes the fixtures do not cover.  Tolerances per north_star."""
+import os
+
+import numpy as np
+import pytest
+
+import np_minidiff as orc
+from conftest import GOLDEN, ulp_diff
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def md():
+    import minidiff_b200 as md
+
+    md.backend.assert_live()
+    return md
+
+
+def close(got, want, rtol=1e-4, atol=1e-5):
+    got = got.as_numpy() if hasattr(got, "as_numpy") else np.asarray(got)
+    want = np.asarray(want)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    assert got.dtype == want.dtype, (got.dtype, want.dtype)
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=atol)
+
+
+def ulps(got, want, n=2):
+    got = got.as_numpy()
+    assert got.shape == want.shape and got.dtype == want.dtype
+    assert ulp_diff(got, want).max(initial=0) <= n
+
+
+# ------------------------------------------------------------------ C1: README example
+def run_c1(md):
+    x = md.Tensor([[0, 2, -2, 1], [-1, -1, -2, -2]], allow_grad=True, dtype=md.float32)
+    y = md.Tensor([[2, 3, 4, 5], [0, -1, -3, 2]], allow_grad=True, dtype=md.float32)
+    f = 2 * y * md.sin(x) - x**2
+    f.backward(allow_higher_order=True)
+    out = {"f": f.as_numpy(), "dx": x.grad.as_numpy(), "dy": y.grad.as_numpy()}
+    x.grad.backward()
+    out["dxx"], out["dxy"] = x.grad.as_numpy(), y.grad.as_numpy()
+    return out
+
+
+def test_c1_readme_first_and_second_order(md, golden):
+    g = golden("c1.npz")
+    r = run_c1(md)
+    for k in ("f", "dx", "dy", "dxx", "dxy"):
+        assert r[k].dtype == np.float32 and r[k].shape == (2, 4)
+        assert ulp_diff(r[k], g[k]).max() <= 2, k
+
+
+def test_c1_default_dtype_follows_numpy(md):
+    x = md.Tensor([[0, 2, -2, 1]], allow_grad=True)          # README literal ints -> int64
+    assert x.dtype == np.int64
+    f = 2 * x * md.sin(x)
+    assert f.dtype == np.float64
+
+
+# ------------------------------------------------------------------ C2: broadcast chain
+def run_c2(md, a_np, c_np, higher=False):
+    a = md.Tensor(a_np.copy(), allow_grad=True)
+    c = md.Tensor(c_np.copy(), allow_grad=True)
+    z = md.sin(a * c + a) ** 2
+    loss = md.sum(z)
+    loss.backward(allow_higher_order=higher) if higher else loss.backward()
+    return loss, a, c
+
+
+@pytest.mark.parametrize("n,m", [(64, 48), (257, 131), (1024, 1024)])
+def test_c2_vs_golden(md, golden, n, m):
+    g = golden(f"c2_{n}x{m}.npz")
+    loss, a, c = run_c2(md, g["a"], g["c"])
+    assert loss.shape == () and a.grad.shape == (n, 1) and c.grad.shape == (1, m)
+    close(loss, g["loss"], rtol=1e-4)
+    close(a.grad, g["da"], rtol=1e-4, atol=1e-5 * np.sqrt(m))
+    close(c.grad, g["dc"], rtol=1e-4, atol=1e-5 * np.sqrt(n))
+
+
+def test_c2_unfused_reference_chain_matches_fused(md, golden):
+    """allow_higher_order=True disables the fused handlers (every grad op is recorded, like the
+    reference): both routes must agree."""
+    g = golden("c2_257x131.npz")
+    _, a1, c1 = run_c2(md, g["a"], g["c"], higher=False)
+    _, a2, c2 = run_c2(md, g["a"], g["c"], higher=True)
+    close(a1.grad, a2.grad.as_numpy(), rtol=1e-5, atol=1e-4)
+    close(c1.grad, c2.grad.as_numpy(), rtol=1e-5, atol=1e-4)
+
+
+def test_c2_vs_oracle_medium(md):
+    a_np, c_np = orc.config2_inputs(2048, 3072)
+    want = orc.config2(a_np, c_np)
+    loss, a, c = run_c2(md, a_np, c_np)
+    truth_scale = np.sqrt(3072)
+    close(loss, want["loss"], rtol=1e-4)
+    close(a.grad, want["da"], rtol=1e-4, atol=2e-5 * truth_scale)
+    close(c.grad, want["dc"], rtol=1e-4, atol=2e-5 * truth_scale)
+
+
+def test_c2_full_size_properties(md):
+    """BASELINE size (2^26 elements): size-independent properties instead of a CPU recomputation:
+    linearity of the gradient in the upstream seed and agreement of loss with a two-block split."""
+    n = m = 8192
+    a_np, c_np = orc.config2_inputs(n, m)
+    loss, a, c = run_c2(md, a_np, c_np)
+    l_full = float(loss.item())
+    parts = 0.0
+    for lo, hi in ((0, n // 2), (n // 2, n)):
+        l, _, _ = run_c2(md, a_np[lo:hi], c_np)
+        parts += float(l.item())
+    assert abs(l_full - parts) <= 1e-5 * abs(l_full)
+    # row block gradients of `a` must equal the corresponding rows of the full gradient
+    _, a_half, _ = run_c2(md, a_np[: n // 2], c_np)
+    np.testing.assert_allclose(a.grad.as_numpy()[: n // 2], a_half.grad.as_numpy(), rtol=1e-5, atol=1e-3)
+    # oracle on a row sample (finishes in well under a second)
+    want = orc.config2(a_np[:64], c_np)
+    np.testing.assert_allclose(a.grad.as_numpy()[:64], want["da"], rtol=1e-4, atol=1e-3)
+
+
+# ------------------------------------------------------------------ C3: matmul fwd + both grads
+@pytest.mark.parametrize("shape", ["48x40x56", "256x384x128"])
+def test_c3_vs_golden(md, golden, shape):
+    g = golden(f"c3_{shape}.npz")
+    A, B = md.Tensor(g["A"], allow_grad=True), md.Tensor(g["B"], allow_grad=True)
+    C = A @ B
+    C.backward()
+    K = g["A"].shape[1]
+    close(C, g["C"], atol=1e-5 * np.sqrt(K))
+    close(A.grad, g["dA"], atol=1e-5 * np.sqrt(g["B"].shape[1]))
+    close(B.grad, g["dB"], atol=1e-5 * np.sqrt(g["A"].shape[0]))
+
+
+@pytest.mark.parametrize("n", [1024, 2048])
+def test_c3_vs_float64(md, n):
+    A_np = np.random.default_rng(1234).standard_normal((n, n)).astype(np.float32)
+    B_np = np.random.default_rng(1235).standard_normal((n, n)).astype(np.float32)
+    A, B = md.Tensor(A_np, allow_grad=True), md.Tensor(B_np, allow_grad=True)
+    C = A @ B
+    C.backward()
+    A64, B64 = A_np.astype(np.float64), B_np.astype(np.float64)
+    ones = np.ones((n, n))
+    tol = dict(rtol=1e-4, atol=1e-5 * np.sqrt(n))
+    np.testing.assert_allclose(C.as_numpy(), A64 @ B64, **tol)
+    np.testing.assert_allclose(A.grad.as_numpy(), ones @ B64.T, **tol)
+    np.testing.assert_allclose(B.grad.as_numpy(), A64.T @ ones, **tol)
+
+
+# ------------------------------------------------------------------ C4: MLP training step
+DIMS, BATCH = (16, 32, 32, 8), 64
+
+
+def relu(md, h):
+    return md.where(h > 0, h, 0)
+
+
+def mlp(md, X, ps):
+    h = X
+    n = len(ps) // 2
+    for l in range(n):
+        h = h @ ps[2 * l] + ps[2 * l + 1]
+        if l < n - 1:
+            h = relu(md, h)
+    return h
+
+
+def run_c4(md, X_np, Y_np, ps_np, lr=0.01):
+    X, Y = md.Tensor(X_np), md.Tensor(Y_np)
+    ps = [md.Tensor(p.copy(), allow_grad=True) for p in ps_np]
+    loss = md.mean((mlp(md, X, ps) - Y) ** 2)
+    loss.backward()
+    grads = [p.grad.as_numpy() for p in ps]
+    with md.no_grad():
+        for p in ps:
+            p -= lr * p.grad
+    return loss, grads, ps
+
+
+def test_c4_vs_golden(md, golden):
+    g = golden("c4.npz")
+    X, Y = orc.mlp_data(BATCH, DIMS[0], DIMS[-1])
+    loss, grads, ps = run_c4(md, X, Y, orc.mlp_params(DIMS))
+    close(loss, g["loss"])
+    for i in range(6):
+        close(grads[i], g[f"g{i}"])
+        close(ps[i], g[f"p{i}"])
+
+
+def test_c4_vs_oracle_wide(md):
+    dims, B = (256, 512, 512, 128), 1024
+    X, Y = orc.mlp_data(B, dims[0], dims[-1])
+    ps_np = orc.mlp_params(dims)
+    want = orc.config4_step(X, Y, ps_np)
+    loss, grads, ps = run_c4(md, X, Y, ps_np)
+    close(loss, want["loss"])
+    for i in range(6):
+        close(grads[i], want["grads"][i], atol=1e-6)
+        close(ps[i], want["params"][i], atol=1e-6)
+    # in-place update did not re-allocate parameter storage, graph refs behave like the reference
+    assert all(p.grad is not None for p in ps)
+
+
+def test_c4_param_update_requires_no_grad(md):
+    X, Y = orc.mlp_data(8, DIMS[0], DIMS[-1])
+    ps = [md.Tensor(p, allow_grad=True) for p in orc.mlp_params(DIMS)]
+    loss = md.mean((mlp(md, md.Tensor(X), ps) - md.Tensor(Y)) ** 2)
+    loss.backward()
+    with pytest.raises(ValueError):
+        ps[0] -= 0.01 * ps[0].grad       # reference: graph_refs never drop on leaves
+
+
+# ------------------------------------------------------------------ C5: Hessian-vector product
+def run_c5(md, X_np, Y_np, ps_np, vs_np):
+    X, Y = md.Tensor(X_np), md.Tensor(Y_np)
+    ps = [md.Tensor(p.copy(), allow_grad=True) for p in ps_np]
+    vs = [md.Tensor(v) for v in vs_np]
+    out = mlp(md, X, ps)
+    L = ((out - Y) ** 2) / float(out.size)
+    L.backward(allow_higher_order=True)
+    g1 = [p.grad.as_numpy() for p in ps]
+    s = None
+    for p, v in zip(ps, vs):
+        t = md.sum(p.grad * v)
+        s = t if s is None else s + t
+    s.backward()
+    return g1, [p.grad.as_numpy() for p in ps]
+
+
+def test_c5_hvp_vs_golden(md, golden):
+    g = golden("c5.npz")
+    X, Y = orc.mlp_data(BATCH, DIMS[0], DIMS[-1])
+    g1, hv = run_c5(md, X, Y, orc.mlp_params(DIMS), [g[f"v{i}"] for i in range(6)])
+    for i in range(6):
+        close(g1[i], g[f"g{i}"], atol=1e-6)
+        close(hv[i], g[f"hv{i}"], atol=1e-6)
+
+
+def test_c5_hvp_vs_oracle_and_float64(md):
+    dims, B = (64, 128, 128, 32), 256
+    X, Y = orc.mlp_data(B, dims[0], dims[-1])
+    ps_np = orc.mlp_params(dims)
+    vs_np = [np.random.default_rng(100 + i).standard_normal(p.shape).astype(np.float32)
+             for i, p in enumerate(ps_np)]
+    want = orc.config5_hvp(X, Y, ps_np, vs_np)
+    truth = orc.config5_hvp(X.astype(np.float64), Y.astype(np.float64),
+                            [p.astype(np.float64) for p in ps_np],
+                            [v.astype(np.float64) for v in vs_np])
+    g1, hv = run_c5(md, X, Y, ps_np, vs_np)
+    for i in range(6):
+        close(hv[i], want["hv"][i], rtol=1e-3, atol=1e-6)
+        np.testing.assert_allclose(hv[i], truth["hv"][i], rtol=1e-3, atol=1e-6)
+
+
+def test_scalar_loss_second_order_raises_like_reference(md):
+    """SURVEY finding 1: reducing to a scalar before a higher-order backward raises in the
+    reference (unbroadcast's gradient is wrong for up-broadcasts); same behaviour here."""
+    x = md.Tensor(np.arange(6, dtype=np.float32).reshape(2, 3), allow_grad=True)
+    loss = md.sum(x ** 3)
+    loss.backward(allow_higher_order=True)
+    with pytest.raises(ValueError):
+        md.sum(x.grad * x.grad).backward()
+
+
+# ------------------------------------------------------------------ per-op golden vectors
+_D = np.load(os.path.join(GOLDEN, "ops.npz"))
+_NAMES = sorted({k.split("/")[0] for k in _D.files})
+
+
+def _funcs(md):
+    F = {
+        "neg": lambda t: -t, "where_relu": lambda t: md.where(t > 0, t, 0),
+        "where_tt": lambda t, u: md.where(t > u, t, u), "clip": lambda t: md.clip(t, -0.5, 0.5),
+        "clip_lo": lambda t: md.clip(t, 0, None), "mask_mul": lambda t: t * (t > 0),
+        "sum_all": md.sum, "mean_all": md.mean, "max_all": md.max,
+        "sum_ax0": lambda t: md.sum(t, axis=(0,)),
+        "sum_ax1_keep": lambda t: md.sum(t, axis=(1,), keepdims=True),
+        "sum_ax02": lambda t: md.sum(t, axis=(0, 2)), "max_ax1": lambda t: md.max(t, axis=1),
+        "min_ax1": lambda t: md.min(t, axis=1), "prod_ax0": lambda t: md.prod(t, axis=0),
+        "T_matmul": lambda t, u: t.T @ u, "reshape": lambda t: md.reshape(t, (7, 5)),
+        "broadcast_to": lambda t: md.broadcast_to(t, (4, 5, 7)),
+        "expand_dims": lambda t: md.expand_dims(t, 1), "swapaxes": lambda t: md.swapaxes(t, 0, 2),
+        "flip": lambda t: md.flip(t, axis=1), "getitem_slice": lambda t: t[1:4, ::2],
+        "getitem_int": lambda t: t[2], "tensordot": lambda t, u: md.tensordot(t, u, axes=1),
+        "mod": lambda t: md.mod(t, 0.75), "std_ax1": lambda t: md.std(t, axis=(1,)),
+        "chain_bcast": lambda a, c: md.sin(a * c + a) ** 2, "power_tt": md.power,
+    }
+    for n in ("add", "subtract", "multiply", "true_divide"):
+        f = getattr(md, n)
+        F[n + "_bcast_col_row"] = f
+        F[n + "_bcast_vec"] = f
+        F[n + "_scalar_l"] = (lambda f: lambda t: f(2.5, t))(f)
+        F[n + "_scalar_r"] = (lambda f: lambda t: f(t, 2.5))(f)
+    for e in (2, 1, 0, 0.5, -1, 3, 2.5):
+        F[f"power_{e}"] = (lambda e: lambda t: t ** e)(e)
+    return F
+
+
+@pytest.mark.parametrize("name", _NAMES)
+def test_op_vectors_forward_and_backward(md, name):
+    fn = _funcs(md).get(name) or getattr(md, name)
+    ins, i = [], 0
+    while f"{name}/in{i}" in _D.files:
+        ins.append(_D[f"{name}/in{i}"]); i += 1
+    ts = [md.Tensor(v.copy(), allow_grad=True) for v in ins]
+    out = fn(*ts)
+    want = _D[f"{name}/out"]
+    got = out.as_numpy()
+    assert got.shape == want.shape and got.dtype == want.dtype, (got.shape, want.shape, got.dtype, want.dtype)
+    if want.dtype == np.float32:
+        loose = name in ("matmul", "T_matmul", "tensordot", "dot", "std_ax1", "prod_ax0") or name.startswith(("sum", "mean"))
+        if loose:
+            np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5)
+        else:
+            assert ulp_diff(got, want).max(initial=0) <= 2, ulp_diff(got, want).max()
+    else:
+        np.testing.assert_array_equal(got, want)
+    if out.allow_grad and not out.is_leaf:
+        w = md.Tensor(np.random.default_rng(11).standard_normal(out.shape).astype(out.dtype))
+        if f"{name}/raises" in _D.files:
+            with pytest.raises(Exception) as ei:
+                md.sum(out * w).backward()
+            assert type(ei.value).__name__ == str(_D[f"{name}/raises"]), ei.value
+            return
+        md.sum(out * w).backward()
+        for j, t in enumerate(ts):
+            if f"{name}/g{j}" in _D.files:
+                gw = _D[f"{name}/g{j}"]
+                gg = t.grad.as_numpy()
+                assert gg.shape == gw.shape and gg.dtype == gw.dtype, (name, j, gg.dtype, gw.dtype)
+                np.testing.assert_allclose(gg, gw, rtol=1e-4, atol=1e-5)
+            else:
+                assert t.grad is None
+
+
+# ------------------------------------------------------------------ finite-difference checks
+FD_OPS = ["sin", "cos", "exp", "tanh", "sinh", "cosh", "absolute", "copy"]
+
+
+@pytest.mark.parametrize("name", FD_OPS)
+def test_first_order_fd_through_utils(md, name):
+    """reference tests/test_ops.py:25-62 harness: loss = sum((0 - f(x))**2)/2, h = 1e-2,
+    rtol 1e-3 / atol 1e-4, float64 inputs (NumPy-default dtype of md.randn)."""
+    from minidiff_b200.utils import compute_grads
+
+    md.backend.seed(3)
+    x = md.randn(2, 2, 2, 2, allow_grad=True)
+    op = getattr(md, name)
+
+    def loss(t):
+        actual = op(t)
+        return md.sum((md.zeros_like(actual) - actual) ** 2) / 2
+
+    manual, auto = compute_grads(x, func=loss, h=1e-2)
+    np.testing.assert_allclose(manual[0].as_numpy(), auto[0].as_numpy(), rtol=1e-3, atol=1e-4)
+
+
+def test_fd_binary_broadcast_and_matmul(md):
+    from minidiff_b200.utils import compute_grads
+
+    md.backend.seed(5)
+    a, b = md.randn(3, 1, allow_grad=True), md.randn(1, 4, allow_grad=True)
+    manual, auto = compute_grads(a, b, func=lambda p, q: md.sum(md.sin(p * q + p) ** 2), h=1e-3)
+    for m_, a_ in zip(manual, auto):
+        np.testing.assert_allclose(m_.as_numpy(), a_.as_numpy(), rtol=1e-3, atol=1e-4)
+    x, y = md.randn(5, 6, allow_grad=True), md.randn(6, 4, allow_grad=True)
+    manual, auto = compute_grads(x, y, func=lambda p, q: md.sum((p @ q) ** 2) / 2, h=1e-3)
+    for m_, a_ in zip(manual, auto):
+        np.testing.assert_allclose(m_.as_numpy(), a_.as_numpy(), rtol=1e-3, atol=1e-4)
+
+
+def test_second_order_fd(md):
+    """d/dx of the autodiff gradient, checked by central differences of the first-order gradient."""
+    x0 = np.random.default_rng(2).standard_normal((3, 4))
+
+    def grad_at(v):
+        x = md.Tensor(v, allow_grad=True)
+        f = md.sin(x) * x ** 3
+        f.backward()
+        return x.grad.as_numpy()
+
+    x = md.Tensor(x0, allow_grad=True)
+    f = md.sin(x) * x ** 3
+    f.backward(allow_higher_order=True)
+    x.grad.backward()
+    h = 1e-5
+    fd = (grad_at(x0 + h) - grad_at(x0 - h)) / (2 * h)       # f is elementwise: Hessian is diagonal
+    np.testing.assert_allclose(x.grad.as_numpy(), fd, rtol=1e-6, atol=1e-6)
+
+
+def test_grad_aliasing_and_accumulation_semantics(md):
+    """SURVEY finding 3: identity gradients alias; fused in-place accumulation must not corrupt
+    aliased buffers nor a user's saved reference."""
+    a = md.Tensor(np.ones((4, 4), np.float32), allow_grad=True)
+    b = md.Tensor(np.full((4, 4), 2, np.float32), allow_grad=True)
+    f = a + b
+    f.backward(retain_grads=True)
+    assert a.grad is b.grad is f.grad
+    g = (a * b + a * a + a)
+    g.backward()
+    np.testing.assert_array_equal(a.grad.as_numpy(), np.full((4, 4), 2 + 2 + 1, np.float32))
+    np.testing.assert_array_equal(b.grad.as_numpy(), np.ones((4, 4), np.float32))
+    keep = a.grad
+    snapshot = keep.as_numpy().copy()
+    (a * 3).backward(reset_grads=False)                     # accumulates on top
+    np.testing.assert_array_equal(a.grad.as_numpy(), snapshot + 3)
+    np.testing.assert_array_equal(keep.as_numpy(), snapshot)  # user's reference untouched
+    s = md.sum(a)
+    s.backward()
+    assert a.grad._data.strides == (0, 0) and not a.grad._data.writeable
+
+
+def test_reuse_graph_cache_gives_same_grads(md):
+    x_np = np.random.default_rng(0).standard_normal((6, 5)).astype(np.float32)
+
+    def step(x):
+        y = md.sum(md.sin(x) * x + x)
+        y.backward()
+        return x.grad.as_numpy()
+
+    plain = step(md.Tensor(x_np, allow_grad=True))
+    with md.reuse_graph():
+        c1 = step(md.Tensor(x_np, allow_grad=True))
+        c2 = step(md.Tensor(x_np, allow_grad=True))
+    np.testing.assert_array_equal(plain, c1)
+    np.testing.assert_array_equal(plain, c2)
+
+
+def test_custom_op_via_create_op_func(md):
+    """README 'Custom Functions': as_minidiff + create_op_func on a backend function."""
+    B = md.backend
+    softsign = md.create_unary_op_func(
+        forward_func=md.as_minidiff(lambda a: B.true_divide(a, B.add(B.absolute(a), 1))),
+        grad=lambda x, grad: grad / (md.absolute(x) + 1) ** 2, op_name="softsign")
+    x_np = np.linspace(-2, 2, 9, dtype=np.float32)
+    x = md.Tensor(x_np, allow_grad=True)
+    y = softsign(x)
+    y.backward()
+    np.testing.assert_allclose(y.as_numpy(), x_np / (np.abs(x_np) + 1), rtol=1e-6)
+    np.testing.assert_allclose(x.grad.as_numpy(), 1 / (np.abs(x_np) + 1) ** 2, rtol=1e-6)
