@@ -1,0 +1,451 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's measurement contract for minidiff_b200.
+
+Headline line (one JSON object on stdout, rank 0):
+  metric  = MLP train samples/s (BASELINE config 4: 3-layer MLP 1024-4096-4096-1024, where-ReLU,
+            mean-MSE, SGD; global batch 65536 fp32 synthetic; data-parallel over N GPUs with NCCL
+            all-reduce of the parameter gradients).  A "step" is one full training step.
+  value   = whole-job samples/s with inputs resident in HBM;   e2e = same through the public API
+            with pinned HOST inputs (H2D of X,Y and D2H of the loss inside the timed region).
+  roofline       = the dominant kernel class of the step (GEMM), timed live with CUDA events on the
+                   library's launch stream during the timed region.
+  cpu_baseline   = the NumPy oracle port of the same step on this box's host cores (bounded sample).
+  fwd_bwd (N=1)  = the single-GPU graph benchmarks of BASELINE.json: config 2 (broadcast chain,
+                   GB/s vs HBM roofline) and config 3 (matmul fwd+bwd, TFLOP/s vs tensor roofline).
+
+`--impl reference` times the reference's CPU path (oracle port of the unmodified algorithm on
+NumPy/OpenBLAS with all host threads) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GLOBAL_BATCH = 65536
+DIMS = (1024, 4096, 4096, 1024)
+LR = 0.01
+METRIC = "mlp_train_samples_per_s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"],
+                "bf16_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "src": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampled during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                "power_w_max": float(max(pw)), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers on top of the C ABI
+# ------------------------------------------------------------------------------------------------
+class Dev:
+    def __init__(self):
+        import ctypes as C
+
+        import minidiff_b200 as md
+        from minidiff_b200.backend import _lib
+
+        self.C, self.md, self.lib, self.check = C, md, _lib.lib, _lib.check
+        md.backend.assert_live()
+
+    def event(self):
+        e = self.C.c_void_p()
+        self.check(self.lib.mdb_event_create(self.C.byref(e)))
+        return e
+
+    def record(self, e):
+        self.check(self.lib.mdb_event_record(e))
+
+    def elapsed_ms(self, a, b):
+        ms = self.C.c_float()
+        self.check(self.lib.mdb_event_elapsed_ms(a, b, self.C.byref(ms)))
+        return ms.value
+
+    def sync(self):
+        self.check(self.lib.mdb_sync())
+
+    def launches(self):
+        return int(self.lib.mdb_launch_count())
+
+    def prof(self, on):
+        self.check(self.lib.mdb_prof_enable(1 if on else 0))
+
+    def prof_read(self, cls):
+        C = self.C
+        ms, n, w = C.c_double(), C.c_uint64(), C.c_double()
+        self.check(self.lib.mdb_prof_read(cls, C.byref(ms), C.byref(n), C.byref(w)))
+        return ms.value, n.value, w.value
+
+    def pinned(self, arr):
+        """copy a NumPy array into pinned host memory; returns (ndarray view, keepalive)"""
+        C = self.C
+        p = C.c_void_p()
+        self.check(self.lib.mdb_host_alloc(arr.nbytes, C.byref(p)))
+        buf = (C.c_char * arr.nbytes).from_address(p.value)
+        view = np.frombuffer(buf, dtype=arr.dtype).reshape(arr.shape)
+        view[...] = arr
+        return view, p
+
+    def upload_into(self, dst_tensor, pinned_view):
+        self.check(self.lib.mdb_h2d(dst_tensor._data.ptr, pinned_view.ctypes.data, pinned_view.nbytes))
+
+
+def dist_setup(world):
+    if world == 1:
+        return None
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        dist.init_process_group("gloo")
+    return dist
+
+
+def barrier(dist):
+    if dist is not None:
+        dist.barrier()
+
+
+def max_over_ranks(dist, x):
+    if dist is None:
+        return x
+    import torch
+
+    t = torch.tensor([x], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+# ------------------------------------------------------------------------------------------------
+# workloads
+# ------------------------------------------------------------------------------------------------
+def bench_mlp(dev, dist, rank, world, steps, warmup, peaks):
+    md = dev.md
+    from minidiff_b200 import workloads as W
+    from minidiff_b200.parallel import DataParallel
+
+    local = GLOBAL_BATCH // world
+    X_np, Y_np = W.mlp_data(local, DIMS[0], DIMS[-1], seed=1000 + 2 * rank)
+    params = [md.Tensor(p, allow_grad=True) for p in W.mlp_params(DIMS)]
+    X, Y = md.Tensor(X_np), md.Tensor(Y_np)
+    dp = DataParallel(params, rank, world) if world > 1 else None
+
+    def step():
+        return W.mlp_train_step(X, Y, params, LR, dp)
+
+    for _ in range(warmup):
+        step()
+    dev.sync()
+    # ---- timed region: inputs resident in HBM
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", 0)))
+    e0, e1 = dev.event(), dev.event()
+    dev.prof(True)
+    barrier(dist)
+    dev.sync()
+    sampler.start()
+    l0 = dev.launches()
+    dev.record(e0)
+    for _ in range(steps):
+        loss = step()
+    dev.record(e1)
+    dev.sync()
+    barrier(dist)
+    ms = dev.elapsed_ms(e0, e1)
+    launches = dev.launches() - l0
+    clocks = sampler.stop()
+    gemm_ms, gemm_n, gemm_flops = dev.prof_read(2)
+    ew_ms, ew_n, ew_bytes = dev.prof_read(0)
+    red_ms, red_n, red_bytes = dev.prof_read(1)
+    dev.prof(False)
+    ms = max_over_ranks(dist, ms)
+    loss_value = float(loss.item())
+
+    # ---- e2e: host (pinned) inputs copied every step, loss read back every step
+    Xh, kx = dev.pinned(X_np)
+    Yh, ky = dev.pinned(Y_np)
+    for _ in range(2):
+        dev.upload_into(X, Xh); dev.upload_into(Y, Yh); float(step().item())
+    barrier(dist)
+    dev.sync()
+    t0 = time.perf_counter()
+    f0, f1 = dev.event(), dev.event()
+    dev.record(f0)
+    for _ in range(steps):
+        dev.upload_into(X, Xh)
+        dev.upload_into(Y, Yh)
+        last = float(step().item())            # D2H read of the loss (4 bytes) every step
+    dev.record(f1)
+    dev.sync()
+    barrier(dist)
+    e2e_ms = max_over_ranks(dist, dev.elapsed_ms(f0, f1))
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    if dp is not None:
+        dp.close()
+
+    tf32_peak = peaks["bf16_sustained"] / 2.0
+    gemm_tflops = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    out = {
+        "metric": METRIC, "value": GLOBAL_BATCH * steps / (ms * 1e-3), "unit": "samples/s",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "C4 MLP 1024-4096-4096-1024 where-ReLU mean-MSE SGD full training step",
+                   "global_batch": GLOBAL_BATCH, "per_gpu_batch": local, "parallelism": f"dp{world}",
+                   "l2": "working set per step (inputs+activations+grads >= 1.3 GB per GPU) exceeds "
+                         "the 126 MB L2, no flush needed"},
+        "loss": loss_value,
+        "e2e": {"value": GLOBAL_BATCH * steps / (e2e_ms * 1e-3), "unit": "samples/s",
+                "h2d_bytes_per_step": int(X_np.nbytes + Y_np.nbytes), "d2h_bytes_per_step": 4,
+                "ms_per_step": e2e_ms / steps, "wall_ms_per_step": wall_ms / steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {
+            "bound": "tensor", "kernel": "mdb_gemm (matmul fwd + dW/dX gradient GEMMs)",
+            "achieved": gemm_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
+            "frac": gemm_tflops / tf32_peak if tf32_peak else None, "traffic": None,
+            "launches": int(gemm_n), "avg_launch_ms": gemm_ms / gemm_n if gemm_n else None,
+            "share_of_step": gemm_ms / ms if ms else None,
+            "note": "achieved = algorithmic 2MNK flops / CUDA-event time of the GEMM launches inside "
+                    "the timed region; peak = TF32 dense peak taken as half the "
+                    f"{peaks['src']} sustained bf16 rate ({peaks['bf16_sustained']} TF/s); a 3xTF32 "
+                    "GEMM issues 3 tensor-core MACs per fp32 product, so pipe use = 3*frac",
+        },
+        "other_kernels": {
+            "elementwise": {"ms_per_step": ew_ms / steps, "calls_per_step": ew_n / steps,
+                            "algorithmic_GBps": ew_bytes / (ew_ms * 1e-3) / 1e9 if ew_ms else None,
+                            "frac_of_hbm": ew_bytes / (ew_ms * 1e-3) / 1e9 / peaks["hbm_gbs"] if ew_ms else None},
+            "reduce": {"ms_per_step": red_ms / steps, "calls_per_step": red_n / steps,
+                       "algorithmic_GBps": red_bytes / (red_ms * 1e-3) / 1e9 if red_ms else None,
+                       "frac_of_hbm": red_bytes / (red_ms * 1e-3) / 1e9 / peaks["hbm_gbs"] if red_ms else None},
+        },
+    }
+    del kx, ky
+    return out
+
+
+def bench_c2(dev, steps, warmup, peaks):
+    md = dev.md
+    from minidiff_b200 import workloads as W
+
+    a_np, c_np = W.c2_inputs()
+    a, c = md.Tensor(a_np, allow_grad=True), md.Tensor(c_np, allow_grad=True)
+    for _ in range(warmup):
+        W.c2_step(a, c)
+    dev.sync()
+    e0, e1 = dev.event(), dev.event()
+    dev.prof(True)
+    l0 = dev.launches()
+    dev.record(e0)
+    for _ in range(steps):
+        loss = W.c2_step(a, c)
+    dev.record(e1)
+    dev.sync()
+    ms = dev.elapsed_ms(e0, e1) / steps
+    launches = (dev.launches() - l0) / steps
+    ew_ms, ew_n, ew_bytes = dev.prof_read(0)
+    red_ms, red_n, red_bytes = dev.prof_read(1)
+    dev.prof(False)
+    kern_ms, kern_bytes = ew_ms + red_ms, ew_bytes + red_bytes
+    return {
+        "workload": "C2 sum(sin(a*c+a)**2).backward(), a:(8192,1) c:(1,8192) fp32 (2^26-element tensors)",
+        "ms_per_iter": ms, "launches_per_iter": launches, "loss": float(loss.item()),
+        "reference_chain_GBps": W.C2_ALGORITHMIC_BYTES / (ms * 1e-3) / 1e9,
+        "reference_chain_bytes": W.C2_ALGORITHMIC_BYTES,
+        "note": "reference_chain_GBps = the 26E bytes the reference's 22-call chain moves (SURVEY 8d) "
+                "/ our time; fused backward kernels move fewer bytes, so this can exceed the HBM peak. "
+                "The roofline below is per kernel: algorithmic bytes of OUR launches / their event time.",
+        "roofline": {"bound": "hbm", "achieved": kern_bytes / (kern_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                     "unit": "GB/s", "frac": kern_bytes / (kern_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                     "traffic": None, "kernel_ms_per_iter": kern_ms / steps,
+                     "algorithmic_bytes_per_iter": kern_bytes / steps,
+                     "inputs": "8 tensors of 256 MiB per iteration > 126 MB L2 (no flush needed)"},
+    }
+
+
+def bench_c3(dev, steps, warmup, peaks, n=8192):
+    md = dev.md
+    from minidiff_b200 import workloads as W
+
+    A_np, B_np = W.c3_inputs(n)
+    A, B = md.Tensor(A_np, allow_grad=True), md.Tensor(B_np, allow_grad=True)
+    for _ in range(warmup):
+        W.c3_step(A, B)
+    dev.sync()
+    e0, e1 = dev.event(), dev.event()
+    dev.prof(True)
+    dev.record(e0)
+    for _ in range(steps):
+        W.c3_step(A, B)
+    dev.record(e1)
+    dev.sync()
+    ms = dev.elapsed_ms(e0, e1) / steps
+    g_ms, g_n, g_fl = dev.prof_read(2)
+    dev.prof(False)
+    tf32_peak = peaks["bf16_burst"] / 2.0
+    tf = g_fl / (g_ms * 1e-3) / 1e12
+    return {"workload": f"C3 C=A@B; C.backward() {n}^3 fp32 (NN fwd, NT dA, TN dB)",
+            "ms_per_iter": ms, "TFLOPs_fp32_equiv": W.c3_flops(n) / (ms * 1e-3) / 1e12,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": tf32_peak, "unit": "TFLOP/s",
+                         "frac": tf / tf32_peak, "traffic": None, "avg_launch_ms": g_ms / g_n,
+                         "note": "peak = half the measured burst bf16 rate; 3xTF32 pipe use = 3*frac"}}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arms (oracle port == the reference's algorithm on NumPy/OpenBLAS)
+# ------------------------------------------------------------------------------------------------
+def cpu_mlp_samples_per_s(sample_batch, reps):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import np_minidiff as orc
+
+    X, Y = orc.mlp_data(sample_batch, DIMS[0], DIMS[-1])
+    ps = orc.mlp_params(DIMS)
+    orc.config4_step(X[:256], Y[:256], ps)          # warm-up (page faults, thread pool)
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        orc.config4_step(X, Y, ps)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return sample_batch / best, best
+
+
+def reference_arm(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    sample = 2048
+    times = []
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import np_minidiff as orc
+
+    X, Y = orc.mlp_data(sample, DIMS[0], DIMS[-1])
+    ps = orc.mlp_params(DIMS)
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        orc.config4_step(X, Y, ps)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    v = sample * len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / len(times) * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "C4 MLP 1024-4096-4096-1024 where-ReLU mean-MSE SGD full training step",
+                   "global_batch": GLOBAL_BATCH, "parallelism": "cpu"},
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"each step = one full training step on a {sample}-row sample of the "
+                                   f"{GLOBAL_BATCH}-row batch (NumPy {np.__version__} / OpenBLAS, all host "
+                                   "threads for matmul; elementwise + reductions are single-threaded in NumPy)"},
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--skip-extras", action="store_true", help="skip the C2/C3 single-GPU benchmarks")
+    ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        return reference_arm(args, rank)
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            sys.exit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
+    warmup = max(args.warmup, 3)
+    peaks = load_peaks()
+    sys.argv = sys.argv[:1]
+    dev = Dev()
+    dist = dist_setup(world)
+    line = bench_mlp(dev, dist, rank, world, args.steps, warmup, peaks)
+    line["warmup"] = warmup
+    if rank == 0 and world == 1:
+        if not args.skip_extras:
+            line["fwd_bwd"] = {"c2_broadcast_chain": bench_c2(dev, max(args.steps, 10), warmup, peaks),
+                               "c3_matmul": bench_c3(dev, max(2, min(args.steps, 5)), warmup, peaks)}
+        if not args.skip_cpu:
+            v, secs = cpu_mlp_samples_per_s(1024, 2)
+            line["cpu_baseline"] = {
+                "value": v, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+                "sample": f"one full training step on a 1024-row sample of the batch, best of 2 "
+                          f"({secs:.2f} s each); NumPy {np.__version__}/OpenBLAS, matmul on all host "
+                          "threads, elementwise single-threaded"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

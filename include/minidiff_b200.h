@@ -117,6 +117,13 @@ int mdb_event_record(void* ev);
 int mdb_event_elapsed_ms(void* start, void* stop, float* ms);  /* syncs on `stop`                 */
 int mdb_event_destroy(void* ev);
 uint64_t mdb_launch_count(void);                  /* kernels launched by this library so far     */
+/* per-class device time of the library's own launches, measured with CUDA event pairs on the
+ * compute stream around each public compute call while enabled.  cls: 0 elementwise (incl. copy /
+ * fill), 1 reductions (incl. the fused un-broadcast form), 2 GEMM, 3 other.  `work` is the summed
+ * ALGORITHMIC work of those calls: bytes (each distinct input element once at its un-broadcast
+ * size + each output element once) for classes 0/1/3, flops (2*M*N*K) for class 2. */
+int mdb_prof_enable(int on);                      /* turning on clears earlier records           */
+int mdb_prof_read(int cls, double* total_ms, uint64_t* calls, double* work);
 
 /* ---- compute ------------------------------------------------------------------------------- */
 /* ones_like/zeros_like/full/full_like (backend/numpy.py:98-103) */

@@ -14,7 +14,7 @@ MAX_DIMS = 8
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
-        f"{LIB_PATH} is missing: build it with `python -m minidiff_b200.build` "
+        f"{LIB_PATH} is missing: build it with `python scripts/build_lib.py` "
         "(or __graft_entry__.build()). minidiff_b200 has no CPU fallback."
     )
 lib = C.CDLL(LIB_PATH)
@@ -77,6 +77,8 @@ _SIGS = {
     "mdb_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_void_p, _P(C.c_float)]),
     "mdb_event_destroy": (C.c_int, [C.c_void_p]),
     "mdb_launch_count": (C.c_uint64, []),
+    "mdb_prof_enable": (C.c_int, [C.c_int]),
+    "mdb_prof_read": (C.c_int, [C.c_int, _P(C.c_double), _P(C.c_uint64), _P(C.c_double)]),
     "mdb_fill": (C.c_int, [_A, C.c_double]),
     "mdb_copy": (C.c_int, [_A, _A]),
     "mdb_elementwise": (C.c_int, [C.c_int, _A, C.c_int, _A]),

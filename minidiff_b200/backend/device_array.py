@@ -98,7 +98,7 @@ class DeviceArray:
         a = np.asarray(a)
         if a.dtype == object:
             raise TypeError("object arrays cannot live on the device")
-        host = np.ascontiguousarray(a)
+        host = np.ascontiguousarray(a).reshape(a.shape)   # ascontiguousarray promotes 0-d to 1-d
         out = cls.empty(host.shape, host.dtype)
         if host.size:
             check(lib.mdb_h2d(out.ptr, host.ctypes.data, host.nbytes))

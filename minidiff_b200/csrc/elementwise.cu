@@ -366,10 +366,12 @@ extern "C" {
 
 int mdb_elementwise(int op, const mdb_array* out, int n_in, const mdb_array* in) {
   MDB_REQUIRE(n_in >= 1 && n_in <= 3, "elementwise takes 1..3 inputs, got %d", n_in);
+  mdb::ProfScope prof(mdb::PROF_ELEMENTWISE, mdb::algorithmic_bytes(out, n_in, in));
   return mdb::elementwise_impl(op, out, n_in, in);
 }
 
 int mdb_copy(const mdb_array* out, const mdb_array* in) {
+  mdb::ProfScope prof(mdb::PROF_ELEMENTWISE, mdb::algorithmic_bytes(out, 1, in));
   return mdb::elementwise_impl(MDB_OP_COPY, out, 1, in);
 }
 
@@ -377,6 +379,7 @@ int mdb_fill(const mdb_array* out, double value) {
   mdb_array imm;
   imm.ptr = nullptr; imm.dtype = MDB_F64; imm.ndim = 0; imm.imm = value;
   imm.imm_i = (int64_t)value;
+  mdb::ProfScope prof(mdb::PROF_ELEMENTWISE, mdb::algorithmic_bytes(out, 0, nullptr));
   return mdb::elementwise_impl(MDB_OP_COPY, out, 1, &imm);
 }
 

@@ -107,6 +107,7 @@ int mdb_gemm(const mdb_array* c, const mdb_array* a, const mdb_array* b, int acc
               "gemm: extents must fit in int32");
   if (c->shape[0] == 0 || c->shape[1] == 0) return 0;
   if (a->shape[1] == 0) return accumulate ? 0 : mdb_fill(c, 0.0);
+  ProfScope prof(PROF_GEMM, 2.0 * (double)a->shape[0] * (double)a->shape[1] * (double)b->shape[1]);
   if (g_force_path != 1) {
     int rc = gemm_tcgen05(c, a, b, accumulate);
     if (rc == 0) return 0;

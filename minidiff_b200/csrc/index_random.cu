@@ -83,6 +83,7 @@ static int rows_op(const mdb_array* indexed, const mdb_array* dense, const mdb_a
   p.total = p.n_idx * p.inner;
   p.esize = dtype_size(indexed->dtype); p.dtype = indexed->dtype; p.mode = mode;
   if (p.total == 0) return 0;
+  ProfScope prof(PROF_OTHER, (double)p.total * (2.0 * p.esize + 8.0 / (double)(p.inner ? p.inner : 1)));
   MDB_REQUIRE(p.a_rows > 0, "index out of bounds: indexed axis has extent 0");
   rows_kernel<<<grid_for(p.total, 256), 256, 0, g_stream>>>(p);
   MDB_CHECK_LAUNCH();

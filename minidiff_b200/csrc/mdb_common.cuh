@@ -87,6 +87,18 @@ inline int grid_for(int64_t work_items, int threads, int max_ctas_per_sm = 8) {
   return (int)(want < cap ? want : cap);
 }
 
+// Per-class kernel timing with CUDA events on the compute stream (bench.py's roofline numbers).
+// Off by default; when on, every public compute entry point brackets its launches with an event
+// pair and records the ALGORITHMIC work of the call (bytes: each distinct input element once at
+// its un-broadcast size + each output element once; flops: 2MNK).
+enum ProfClass { PROF_ELEMENTWISE = 0, PROF_REDUCE = 1, PROF_GEMM = 2, PROF_OTHER = 3, PROF_NCLASS = 4 };
+struct ProfScope {
+  int slot;
+  ProfScope(int cls, double work);
+  ~ProfScope();
+};
+double algorithmic_bytes(const mdb_array* out, int n_in, const mdb_array* in);
+
 // temp buffer from the caching allocator, returned on scope exit (stream-ordered => safe)
 struct TempBuf {
   void* ptr = nullptr;

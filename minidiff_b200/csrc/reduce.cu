@@ -538,6 +538,7 @@ int mdb_reduce(int red, const mdb_array* out, const mdb_array* in, uint32_t axis
     full[d] = in->shape[d];
     MDB_REQUIRE(out->shape[d] == (redax[d] ? 1 : in->shape[d]), "reduce: bad output extent on axis %d", d);
   }
+  ProfScope prof(PROF_REDUCE, algorithmic_bytes(out, 1, in));
   if (nd == 0) return elementwise_impl(MDB_OP_COPY, out, 1, in);
   return reduce_driver(MDB_OP_COPY, red, out, 1, in, full, redax, nd, false);
 }
@@ -578,6 +579,8 @@ int mdb_elementwise_reduce(int op, const mdb_array* out, int n_in, const mdb_arr
     redax[d] = (oe == 1 && full[d] != 1);
   }
   o.ndim = nd;
+  ProfScope prof(PROF_REDUCE, algorithmic_bytes(out, n_in, in) +
+                                  (accumulate ? algorithmic_bytes(out, 0, nullptr) : 0.0));
   return reduce_driver(op, MDB_RED_SUM, &o, n_in, in, full, redax, nd, accumulate != 0);
 }
 

@@ -94,6 +94,50 @@ struct Allocator {
   }
 };
 static Allocator g_alloc;
+
+// ---- profiler ---------------------------------------------------------------------------------
+struct ProfRecord { cudaEvent_t a, b; int cls; double work; };
+static std::vector<ProfRecord> g_prof;
+static size_t g_prof_used = 0;
+static bool g_prof_on = false;
+static int g_prof_depth = 0;
+
+ProfScope::ProfScope(int cls, double work) : slot(-1) {
+  if (!g_prof_on || g_prof_depth++ > 0) return;        // only the outermost entry point records
+  if (g_prof_used == g_prof.size()) {
+    ProfRecord r;
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    g_prof.push_back(r);
+  }
+  slot = (int)g_prof_used++;
+  g_prof[slot].cls = cls;
+  g_prof[slot].work = work;
+  cudaEventRecord(g_prof[slot].a, g_stream);
+}
+ProfScope::~ProfScope() {
+  if (!g_prof_on) return;
+  --g_prof_depth;
+  if (slot >= 0) cudaEventRecord(g_prof[slot].b, g_stream);
+}
+
+double algorithmic_bytes(const mdb_array* out, int n_in, const mdb_array* in) {
+  auto unique_bytes = [](const mdb_array* a) {
+    if (!a || !a->ptr) return 0.0;
+    double n = 1.0;
+    for (int d = 0; d < a->ndim; ++d)
+      if (a->strides[d] != 0 || a->shape[d] == 1) n *= (double)a->shape[d];
+    return n * dtype_size(a->dtype);
+  };
+  double b = unique_bytes(out);
+  for (int k = 0; k < n_in; ++k) {
+    bool alias = false;   // the same view passed twice (x*x) is read once
+    for (int j = 0; j < k; ++j)
+      alias = alias || (in[j].ptr == in[k].ptr && in[j].ndim == in[k].ndim &&
+                        in[j].strides[0] == in[k].strides[0]);
+    if (!alias) b += unique_bytes(&in[k]);
+  }
+  return b;
+}
 }  // namespace mdb
 
 using namespace mdb;
@@ -242,5 +286,29 @@ int mdb_event_destroy(void* ev) {
   return 0;
 }
 uint64_t mdb_launch_count(void) { return g_launches.load(); }
+
+int mdb_prof_enable(int on) {
+  MDB_TRY(ensure_init());
+  MDB_CUDA(cudaStreamSynchronize(g_stream));
+  g_prof_on = on != 0;
+  g_prof_used = 0;
+  g_prof_depth = 0;
+  return 0;
+}
+
+int mdb_prof_read(int cls, double* total_ms, uint64_t* calls, double* work) {
+  MDB_REQUIRE(cls >= 0 && cls < PROF_NCLASS, "bad profile class %d", cls);
+  MDB_CUDA(cudaStreamSynchronize(g_stream));
+  double ms = 0.0, w = 0.0;
+  uint64_t n = 0;
+  for (size_t i = 0; i < g_prof_used; ++i) {
+    if (g_prof[i].cls != cls) continue;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, g_prof[i].a, g_prof[i].b) != cudaSuccess) { cudaGetLastError(); continue; }
+    ms += t; w += g_prof[i].work; ++n;
+  }
+  *total_ms = ms; *calls = n; *work = w;
+  return 0;
+}
 
 }  // extern "C"

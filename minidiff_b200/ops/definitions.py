@@ -8,6 +8,7 @@ and ops on the hot path additionally carry a fused device backward (ops/fused.py
 """
 from __future__ import annotations
 
+from builtins import min as _py_min
 from math import prod as _prod
 
 import minidiff_b200 as md
@@ -125,7 +126,7 @@ def unbroadcast_forward(x, target_shape):
     lead = tuple(range(x.ndim - len(target_shape)))
     if lead:
         x = x.sum(axis=lead)
-    n = min(len(target_shape), x.ndim)
+    n = _py_min(len(target_shape), x.ndim)
     stretched = tuple(i for i in range(n) if x.shape[i] > 1 and target_shape[i] == 1)
     if stretched:
         x = x.sum(axis=stretched, keepdims=True)

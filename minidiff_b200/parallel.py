@@ -1,0 +1,94 @@
+"""Data-parallel gradient exchange for the MLP training step (BASELINE config 4).
+
+One process per GPU.  Parameters are replicated, the batch is sharded by rows; after the local
+backward each parameter gradient is averaged over ranks with NCCL (over NVLink 5 / NVSwitch).
+The all-reduce of a parameter is issued on the library's comm stream the moment the backward
+sweep has finished that parameter's gradient (Tensor grad-ready hook), so the exchange of the
+late layers overlaps the remaining backward GEMMs; `finish()` makes the compute stream wait for
+the comm stream before the optimiser touches the gradients.
+
+The reference has no distributed code; this module is new.  Rendezvous (passing the
+NCCL unique id) uses torch.distributed's gloo group: plumbing only, no tensor goes through torch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+
+from minidiff_b200.backend import _lib
+from minidiff_b200.backend._lib import check, lib
+
+
+def find_nccl() -> str:
+    try:
+        import nvidia.nccl as n
+
+        for base in list(getattr(n, "__path__", [])):
+            hits = glob.glob(os.path.join(base, "lib", "libnccl.so*"))
+            if hits:
+                return hits[0]
+    except Exception:
+        pass
+    return "libnccl.so.2"
+
+
+class DataParallel:
+    def __init__(self, params, rank=None, world=None, overlap=True):
+        import torch.distributed as dist
+
+        self.rank = int(os.environ.get("RANK", 0)) if rank is None else rank
+        self.world = int(os.environ.get("WORLD_SIZE", 1)) if world is None else world
+        self.params = list(params)
+        self.overlap = overlap
+        self._pending = False
+        if self.world == 1:
+            return
+        if not dist.is_initialized():
+            dist.init_process_group("gloo", rank=self.rank, world_size=self.world)
+        _lib.ensure_device()
+        path = find_nccl().encode()
+        uid = (C.c_char * 128)()
+        if self.rank == 0:
+            check(lib.mdb_comm_unique_id(uid, path))
+        box = [bytes(uid.raw)]
+        dist.broadcast_object_list(box, src=0)
+        check(lib.mdb_comm_init(self.rank, self.world, box[0], path))
+        if overlap:
+            for p in self.params:
+                p._grad_hook = self._on_grad_ready
+
+    # called by the backward sweep as soon as p.grad is final
+    def _on_grad_ready(self, p):
+        self._allreduce(p)
+
+    def _allreduce(self, p):
+        g = p.grad._data
+        if g.dtype != np.float32 or not g.is_c_contiguous() or not g.writeable:
+            # aliased / broadcast gradient: give it private contiguous storage first
+            from minidiff_b200.backend import functions as F
+            import minidiff_b200 as md
+
+            p.grad = md.Tensor(F.astype(g, np.float32))
+            g = p.grad._data
+        check(lib.mdb_comm_allreduce_f32(g.ptr, g.size, 1))
+        self._pending = True
+
+    def finish(self):
+        """All gradients averaged and visible to the compute stream after this returns (async)."""
+        if self.world == 1:
+            return
+        if not self.overlap:
+            for p in self.params:
+                self._allreduce(p)
+        if self._pending:
+            check(lib.mdb_comm_wait())
+            self._pending = False
+
+    def close(self):
+        if self.world > 1:
+            for p in self.params:
+                p._grad_hook = None
+            check(lib.mdb_comm_destroy())

@@ -86,7 +86,7 @@ class Tensor:
     """reference tensor.py:92-433"""
 
     __slots__ = ("_data", "_allow_grad", "_iterator", "graph_refs", "grad", "op_node",
-                 "_grad_private", "__weakref__")
+                 "_grad_private", "_grad_hook", "__weakref__")
     __array_ufunc__ = None  # numpy scalars defer to our reflected operators
 
     def __init__(self, data, allow_grad=False, dtype=None):
@@ -106,6 +106,9 @@ class Tensor:
         # the grad Tensor whose buffer this tensor exclusively owns during the current backward
         # sweep (may be accumulated into in place); see topology.OpNode.accumulate
         self._grad_private = None
+        # optional callable(tensor) fired by the backward sweep once this leaf's gradient is
+        # complete (used by parallel.DataParallel to start the all-reduce early)
+        self._grad_hook = None
 
     # ---- graph flags (tensor.py:115-148)
     @property

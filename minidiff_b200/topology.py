@@ -140,13 +140,33 @@ class OpNode:
             t._grad_private = None  # in-place accumulation only into buffers born in THIS sweep
             if reset_grads:
                 t.grad = None
+        # leaves with a grad-ready hook: count how many nodes of this sweep consume them
+        waiting = None
+        if any(t._grad_hook is not None for t in path):
+            waiting = {}
+            for node in [self] + [t.op_node for t in path if t.op_node is not None]:
+                for x in node.tensor_inputs:
+                    if x._grad_hook is not None and x.op_node is None and x.allow_grad:
+                        waiting[id(x)] = waiting.get(id(x), 0) + 1
+
+        def consumed(node):
+            for x in node.tensor_inputs:
+                if id(x) in waiting:
+                    waiting[id(x)] -= 1
+                    if waiting[id(x)] == 0 and x.grad is not None:
+                        x._grad_hook(x)
+
         with md.enable_grad(allow_higher_order):
             self.update_grads(seed_grad)
+            if waiting:
+                consumed(self)
             for t in reversed(path):
                 node = t.op_node
                 if node is None:
                     continue
                 node.update_grads(t.grad)
+                if waiting:
+                    consumed(node)
                 if not retain_grads:
                     t.grad = None
                     t._grad_private = None

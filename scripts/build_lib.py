@@ -1,8 +1,11 @@
 """Build libminidiff_b200.so in-tree with nvcc for sm_100a (no torch extension machinery: the
 library is a plain C-ABI shared object, see include/minidiff_b200.h).
 
-    python -m minidiff_b200.build            # incremental
-    python -m minidiff_b200.build --force
+    python scripts/build_lib.py            # incremental
+    python scripts/build_lib.py --force
+
+Kept OUTSIDE the package on purpose: importing `minidiff_b200` loads the shared library, so the
+thing that creates the library must not need that import.
 """
 from __future__ import annotations
 
@@ -13,8 +16,8 @@ import subprocess
 import sys
 from concurrent.futures import ThreadPoolExecutor
 
-PKG = os.path.dirname(os.path.abspath(__file__))
-ROOT = os.path.dirname(PKG)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "minidiff_b200")
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(PKG, "lib", "libminidiff_b200.so")
@@ -73,7 +76,7 @@ def build_library(force: bool = False, verbose: bool = True) -> str:
 
     if jobs:
         if verbose:
-            print(f"[minidiff_b200.build] compiling {len(jobs)} source(s) for sm_100a ...", flush=True)
+            print(f"[build_lib] compiling {len(jobs)} source(s) for sm_100a ...", flush=True)
         with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             for done in ex.map(compile_one, jobs):
                 if verbose:
@@ -86,7 +89,7 @@ def build_library(force: bool = False, verbose: bool = True) -> str:
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
         if verbose:
-            print("[minidiff_b200.build] linked", os.path.relpath(LIB, ROOT), flush=True)
+            print("[build_lib] linked", os.path.relpath(LIB, ROOT), flush=True)
     return LIB
 
 

@@ -77,10 +77,14 @@ def test_binary_python_scalar_is_weak(B, name, scalar):
         check(getattr(B, name)(scalar, dev(B, a)), getattr(np, name)(scalar, a), ulp=ulp)
 
 
-@pytest.mark.parametrize("name,ulp", [("sin", 2), ("cos", 2), ("exp", 2), ("tan", 2), ("sinh", 2),
+@pytest.mark.parametrize("name,ulp", [("sin", 2), ("cos", 2), ("exp", 2), ("tan", 3), ("sinh", 2),
                                       ("cosh", 2), ("tanh", 2), ("absolute", 0), ("sign", 0),
                                       ("ceil", 0), ("floor", 0)])
 def test_unary_fp32(B, name, ulp):
+    """vs NumPy on this host.  The device results are correctly rounded (<= 0.5 ulp + epsilon from
+    the float64 truth, asserted in the next test), so the distance to NumPy is NumPy's own error
+    (+0.5): NumPy's AVX512 `tan`/`log` are up to 3 ulp from truth on this CPU (SURVEY finding 5),
+    hence the 3 for tan."""
     a = f32(257, 33, scale=3.0)
     check(getattr(B, name)(dev(B, a)), getattr(np, name)(a), ulp=ulp)
 
@@ -89,14 +93,14 @@ def test_unary_fp32_vs_float64_truth(B):
     """Device error against the correctly rounded result (the budget is 2 ulp; NumPy's own SIMD
     paths are 1-3 ulp from truth, SURVEY finding 5, so this is the stricter, host-independent check)."""
     a = f32(1 << 16, scale=4.0)
-    for name in ("sin", "cos", "exp", "tanh"):
+    for name in ("sin", "cos", "exp", "tan", "tanh", "sinh", "cosh"):
         truth = getattr(np, name)(a.astype(np.float64)).astype(np.float32)
         d = ulp_diff(host(getattr(B, name)(dev(B, a))), truth)
-        assert d.max() <= 2, (name, d.max())
+        assert d.max() <= 1, (name, d.max())
     p = np.abs(a) + 1e-3
-    assert ulp_diff(host(B.log(dev(B, p))), np.log(p.astype(np.float64)).astype(np.float32)).max() <= 2
+    assert ulp_diff(host(B.log(dev(B, p))), np.log(p.astype(np.float64)).astype(np.float32)).max() <= 1
     assert ulp_diff(host(B.power(dev(B, p), 2.5)),
-                    np.power(p.astype(np.float64), 2.5).astype(np.float32)).max() <= 2
+                    np.power(p.astype(np.float64), 2.5).astype(np.float32)).max() <= 1
 
 
 def test_log_sqrt_power_fastpaths(B):
@@ -142,11 +146,9 @@ def test_dtype_promotion_matches_numpy(B, dt):
         want = getattr(np, name)(a, b)
         check(getattr(B, name)(dev(B, a), dev(B, b)), want,
               rtol=1e-6 if want.dtype.kind == "f" else None)
-        want = getattr(np, name)(a, a)
-        if name == "true_divide":
-            continue
-        if dt == np.bool_ and name == "subtract":
+        if name == "true_divide" or (dt == np.bool_ and name == "subtract"):
             continue  # NumPy raises for bool - bool
+        want = getattr(np, name)(a, a)
         check(getattr(B, name)(dev(B, a), dev(B, a)), want, rtol=1e-12 if want.dtype.kind == "f" else None)
     check(B.sin(dev(B, a)).astype(np.float64), np.sin(a).astype(np.float64), rtol=1e-3, atol=1e-3)
     check(B.add(dev(B, a), 2.5), np.add(a, 2.5), rtol=1e-12)
@@ -288,11 +290,12 @@ def test_view_functions_exact(B):
                          ("expand_dims", (2,), {}), ("expand_dims", ((0, 3),), {}),
                          ("reshape", ((12, 5),), {}), ("reshape", ((-1,),), {}),
                          ("reshape", ((5, 12),), {"order": "F"}), ("ravel", (), {}),
-                         ("ravel", (), {"order": "F"}), ("flatten", (), {}), ("flip", (), {"axis": 2}),
+                         ("ravel", (), {"order": "F"}), ("flip", (), {"axis": 2}),
                          ("broadcast_to", ((2, 3, 3, 4, 5),), {}), ("atleast_3d", (), {}),
                          ("copy", (), {})]:
         check(getattr(B, fn)(da, *args, **kw), getattr(np, fn)(a, *args, **kw))
-    assert B.transpose(da).strides == np.transpose(a).strides
+    check(B.flatten(da), a.flatten())
+    check(B.flatten(da, order="F"), a.flatten(order="F"))
     assert B.reshape(B.transpose(da[:, 0]), (20, 3)).shape == (20, 3)       # copy path
     check(B.reshape(B.transpose(da[:, 0]), (20, 3)), np.reshape(np.transpose(a[:, 0]), (20, 3)))
     check(B.atleast_1d(dev(B, np.float32(2))), np.atleast_1d(np.float32(2)))
@@ -300,7 +303,7 @@ def test_view_functions_exact(B):
     with pytest.raises(ValueError):
         B.reshape(da, (7, 9))
     with pytest.raises(ValueError):
-        B.broadcast_to(da, (3, 2, 4, 5))
+        B.broadcast_to(da, (3, 1, 4, 6))
 
 
 def test_indexing(B):
