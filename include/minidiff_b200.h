@@ -78,6 +78,7 @@ typedef enum {
   MDB_OP_POW_BWD,        /* (g*p) * x**(p-1), p = immediate in2   definitions.py:509 */
   MDB_OP_DIV_BWD_Y,      /* g * (-x / y**2)       definitions.py:531  */
   MDB_OP_RELU_MASK_BWD,  /* g * (x > 0)           where-grad_y definitions.py:557 with greater */
+  MDB_OP_POW_BWD_LIN,    /* (g*p) * x : POW_BWD for p == 2 (x**1 == x exactly), chosen by the library */
 } mdb_op;
 
 /* reductions (backend sum/mean/max/min/prod/any/all/argmax/argmin: backend/numpy.py:20-57) */

@@ -48,7 +48,7 @@ OP = dict(
     EQ=41, NE=42, GT=43, GE=44, LT=45, LE=46, AND=47, OR=48, XOR=49,
     WHERE=64, CLIP=65, FMA=66,
     SIN_BWD=96, COS_BWD=97, EXP_BWD=98, LOG_BWD=99, TANH_BWD=100, POW_BWD=101, DIV_BWD_Y=102,
-    RELU_MASK_BWD=103,
+    RELU_MASK_BWD=103, POW_BWD_LIN=104,
 )
 RED = dict(SUM=0, MEAN=1, MAX=2, MIN=3, PROD=4, ANY=5, ALL=6, ARGMAX=7, ARGMIN=8)
 

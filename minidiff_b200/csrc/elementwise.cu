@@ -3,6 +3,7 @@
 //   ew_fast    : fp32 compute, <=3 collapsed dims, unit/zero inner strides -> 128-bit vectorised,
 //                4 independent loads in flight per thread, grid sized in multiples of the SM count
 //   ew_generic : any dtype / any strides (<=8 dims), one element per thread-iteration
+#include <algorithm>
 #include <limits>
 
 #include "ew_ops.cuh"
@@ -107,57 +108,71 @@ int compute_class(int op, const mdb_array* out, int n_in, const mdb_array* in) {
 // ------------------------------------------------------------------------------------------------
 struct FastParams {
   void* out;
-  int64_t os2, os1;
+  int32_t os2, os1;
   FastOperand in[3];
   float aux;
   uint32_t total;  // work items = rows * (inner / VEC)
   FastDiv div_lv, div_d1;
 };
 
-template <int OP, int NIN, int VEC>
-__global__ void __launch_bounds__(256) ew_fast(const FastParams p) {
-  constexpr int U = 4;  // independent work items in flight per thread
+// U independent work items per thread: every load is issued before the first use (memory-level
+// parallelism), then compute + store.  FLAT: the whole problem is one contiguous run, no index
+// decode at all.  CHECK=false is the steady-state body (all U items in range).
+template <int OP, int NIN, int VEC, bool FLAT, bool CHECK>
+__device__ __forceinline__ void ew_fast_body(const FastParams& p, uint32_t base, uint32_t stride) {
+  constexpr int U = 4;
   constexpr bool PRED = op_is_predicate(OP);
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t base = blockIdx.x * blockDim.x + threadIdx.x; base < p.total; base += stride * U) {
-    float v[U][3][VEC];
-    int64_t ooff[U];
+  float v[U][3][VEC];
+  int64_t ooff[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      uint32_t w = base + u * stride;
-      if (w < p.total) {
-        uint32_t row, cv, i2, i1;
+  for (int u = 0; u < U; ++u) {
+    const uint32_t w = base + u * stride;
+    if (!CHECK || w < p.total) {
+      uint32_t i2 = 0, i1 = 0, col;
+      if constexpr (FLAT) {
+        col = w * VEC;
+        ooff[u] = col;
+      } else {
+        uint32_t row, cv;
         p.div_lv.divmod(w, row, cv);
         p.div_d1.divmod(row, i2, i1);
-        uint32_t col = cv * VEC;
-        ooff[u] = (int64_t)i2 * p.os2 + (int64_t)i1 * p.os1 + col;
-#pragma unroll
-        for (int k = 0; k < NIN; ++k) fast_load<VEC>(p.in[k], i2, i1, col, v[u][k]);
+        col = cv * VEC;
+        ooff[u] = (int64_t)(int32_t)i2 * (int64_t)p.os2 + (int64_t)(int32_t)i1 * (int64_t)p.os1 + col;
       }
+#pragma unroll
+      for (int k = 0; k < NIN; ++k) fast_load<VEC>(p.in[k], i2, i1, col, v[u][k]);
     }
+  }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      uint32_t w = base + u * stride;
-      if (w < p.total) {
-        float r[VEC];
+  for (int u = 0; u < U; ++u) {
+    const uint32_t w = base + u * stride;
+    if (!CHECK || w < p.total) {
+      float r[VEC];
 #pragma unroll
-        for (int j = 0; j < VEC; ++j)
-          r[j] = apply<OP, float>(v[u][0][j], NIN > 1 ? v[u][1][j] : 0.f,
-                                  NIN > 2 ? v[u][2][j] : 0.f, p.aux);
-        if constexpr (PRED) {
-          unsigned char* o = (unsigned char*)p.out + ooff[u];
-          if constexpr (VEC == 4)
-            *(uchar4*)o = make_uchar4(r[0] != 0.f, r[1] != 0.f, r[2] != 0.f, r[3] != 0.f);
-          else
-            *o = (unsigned char)(r[0] != 0.f);
-        } else {
-          float* o = (float*)p.out + ooff[u];
-          if constexpr (VEC == 4) *(float4*)o = make_float4(r[0], r[1], r[2], r[3]);
-          else *o = r[0];
-        }
+      for (int j = 0; j < VEC; ++j)
+        r[j] = apply<OP, float>(v[u][0][j], NIN > 1 ? v[u][1][j] : 0.f, NIN > 2 ? v[u][2][j] : 0.f, p.aux);
+      if constexpr (PRED) {
+        unsigned char* o = (unsigned char*)p.out + ooff[u];
+        if constexpr (VEC == 4) *(uchar4*)o = make_uchar4(r[0] != 0.f, r[1] != 0.f, r[2] != 0.f, r[3] != 0.f);
+        else *o = (unsigned char)(r[0] != 0.f);
+      } else {
+        float* o = (float*)p.out + ooff[u];
+        if constexpr (VEC == 4) *(float4*)o = make_float4(r[0], r[1], r[2], r[3]);
+        else *o = r[0];
       }
     }
   }
+}
+
+template <int OP, int NIN, int VEC, bool FLAT>
+__global__ void __launch_bounds__(256) ew_fast(const FastParams p) {
+  constexpr uint32_t U = 4;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  uint32_t base = blockIdx.x * blockDim.x + threadIdx.x;
+  // steady state: all U items of this thread are in range
+  for (; (uint64_t)base + (uint64_t)(U - 1) * stride < p.total; base += stride * U)
+    ew_fast_body<OP, NIN, VEC, FLAT, false>(p, base, stride);
+  if (base < p.total) ew_fast_body<OP, NIN, VEC, FLAT, true>(p, base, stride);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -220,12 +235,17 @@ __global__ void __launch_bounds__(256) ew_generic(const GenParams p) {
   X(MDB_OP_SIN_BWD) X(MDB_OP_COS_BWD) X(MDB_OP_EXP_BWD) X(MDB_OP_LOG_BWD) X(MDB_OP_TANH_BWD)    \
   X(MDB_OP_RELU_MASK_BWD)
 #define MDB_TERNARY_OPS(X)                                                                      \
-  X(MDB_OP_WHERE) X(MDB_OP_CLIP) X(MDB_OP_FMA) X(MDB_OP_POW_BWD) X(MDB_OP_DIV_BWD_Y)
+  X(MDB_OP_WHERE) X(MDB_OP_CLIP) X(MDB_OP_FMA) X(MDB_OP_POW_BWD) X(MDB_OP_DIV_BWD_Y)             \
+  X(MDB_OP_POW_BWD_LIN)
 
 template <int OP, int NIN>
-static int launch_fast(const FastParams& p, int vec, int grid) {
-  if (vec == 4) ew_fast<OP, NIN, 4><<<grid, 256, 0, g_stream>>>(p);
-  else ew_fast<OP, NIN, 1><<<grid, 256, 0, g_stream>>>(p);
+static int launch_fast(const FastParams& p, int vec, bool flat, int grid) {
+  if (vec == 4) {
+    if (flat) ew_fast<OP, NIN, 4, true><<<grid, 256, 0, g_stream>>>(p);
+    else ew_fast<OP, NIN, 4, false><<<grid, 256, 0, g_stream>>>(p);
+  } else {
+    ew_fast<OP, NIN, 1, false><<<grid, 256, 0, g_stream>>>(p);   // unaligned / ragged: rare
+  }
   MDB_CHECK_LAUNCH();
   return 0;
 }
@@ -270,6 +290,7 @@ int elementwise_impl(int op, const mdb_array* out, int n_in, const mdb_array* in
   if (op == MDB_OP_POW_BWD) {
     MDB_REQUIRE(in[2].ptr == nullptr, "POW_BWD needs an immediate exponent");
     aux = in[2].imm - 1.0;
+    if (aux == 1.0) op = MDB_OP_POW_BWD_LIN;   // x**1 == x exactly: (g*2)*x, no pow code in the loop
   }
 
   Collapsed c;
@@ -298,15 +319,19 @@ int elementwise_impl(int op, const mdb_array* out, int n_in, const mdb_array* in
     const size_t osz = pred ? 1 : 4;
     bool v4 = (L % 4 == 0) && aligned(out->ptr, 4 * osz) && os1 % 4 == 0 && os2 % 4 == 0;
     FastParams p;
-    p.out = out->ptr; p.os1 = os1; p.os2 = os2; p.aux = (float)aux;
+    auto fits = [](int64_t x) { return x > -(int64_t(1) << 31) && x < (int64_t(1) << 31); };
+    bool small_strides = fits(os1) && fits(os2);
+    p.out = out->ptr; p.os1 = (int32_t)os1; p.os2 = (int32_t)os2; p.aux = (float)aux;
     for (int k = 0; k < n_in; ++k) {
       FastOperand& o = p.in[k];
       o.ptr = in[k].ptr;
       o.imm = (float)in[k].imm;
       o.kind = in[k].ptr == nullptr ? K_IMM : (in[k].dtype == MDB_F32 ? K_F32 : K_U8);
       o.s0 = (int)c.istr[k][nd - 1];
-      o.s1 = nd >= 2 ? c.istr[k][nd - 2] : 0;
-      o.s2 = nd >= 3 ? c.istr[k][nd - 3] : 0;
+      const int64_t s1 = nd >= 2 ? c.istr[k][nd - 2] : 0, s2 = nd >= 3 ? c.istr[k][nd - 3] : 0;
+      small_strides = small_strides && fits(s1) && fits(s2);
+      o.s1 = (int32_t)s1;
+      o.s2 = (int32_t)s2;
       if (o.kind != K_IMM && o.s0 == 1) {
         size_t esz = o.kind == K_F32 ? 4 : 1;
         v4 = v4 && aligned(o.ptr, 4 * esz) && o.s1 % 4 == 0 && o.s2 % 4 == 0;
@@ -314,19 +339,20 @@ int elementwise_impl(int op, const mdb_array* out, int n_in, const mdb_array* in
     }
     const int vec = v4 ? 4 : 1;
     int64_t items = d2 * d1 * (L / vec);
-    if (items < (int64_t(1) << 31) && d2 * d1 < (int64_t(1) << 31)) {
+    const bool flat = nd == 1;
+    if (small_strides && items < (int64_t(1) << 31) && d2 * d1 < (int64_t(1) << 31)) {
       p.total = (uint32_t)items;
       p.div_lv = FastDiv((uint32_t)(L / vec));
       p.div_d1 = FastDiv((uint32_t)d1);
       int grid = grid_for((items + 3) / 4, 256);
       switch (op) {
-#define X(OPID) case OPID: return launch_fast<OPID, 1>(p, vec, grid);
+#define X(OPID) case OPID: return launch_fast<OPID, 1>(p, vec, flat, grid);
         MDB_UNARY_OPS(X)
 #undef X
-#define X(OPID) case OPID: return launch_fast<OPID, 2>(p, vec, grid);
+#define X(OPID) case OPID: return launch_fast<OPID, 2>(p, vec, flat, grid);
         MDB_BINARY_OPS(X)
 #undef X
-#define X(OPID) case OPID: return launch_fast<OPID, 3>(p, vec, grid);
+#define X(OPID) case OPID: return launch_fast<OPID, 3>(p, vec, flat, grid);
         MDB_TERNARY_OPS(X)
 #undef X
         default: return set_error(MDB_EINVAL, "unknown elementwise op %d", op);

@@ -129,7 +129,8 @@ __host__ __device__ constexpr bool op_float_only(int op) {
   return (op >= MDB_OP_SIN && op <= MDB_OP_RECIP) || op == MDB_OP_ISNAN || op >= MDB_OP_SIN_BWD;
 }
 __host__ __device__ constexpr int op_arity(int op) {
-  if (op >= MDB_OP_SIN_BWD) return (op == MDB_OP_POW_BWD || op == MDB_OP_DIV_BWD_Y) ? 3 : 2;
+  if (op >= MDB_OP_SIN_BWD)
+    return (op == MDB_OP_POW_BWD || op == MDB_OP_DIV_BWD_Y || op == MDB_OP_POW_BWD_LIN) ? 3 : 2;
   return op < 32 ? 1 : (op < 64 ? 2 : 3);
 }
 
@@ -204,6 +205,7 @@ __device__ __forceinline__ T apply(T a, T b, T c, T d) {
   }
   else if constexpr (OP == MDB_OP_DIV_BWD_Y) return mul_(a, div_(mul_(T(-1), b), mul_(c, c)));
   else if constexpr (OP == MDB_OP_RELU_MASK_BWD) return mul_(a, T(b > 0));
+  else if constexpr (OP == MDB_OP_POW_BWD_LIN) return mul_(mul_(a, c), b);
   else return a;
 }
 
@@ -247,7 +249,7 @@ enum { K_IMM = 0, K_F32 = 1, K_U8 = 2 };
 
 struct FastOperand {
   const void* ptr;
-  int64_t s2, s1;  // outer strides (elements)
+  int32_t s2, s1;  // outer strides (elements); 32-bit so offsets are single IMAD.WIDE instructions
   int s0;          // inner stride: 0 or 1
   int kind;
   float imm;
@@ -260,7 +262,7 @@ __device__ __forceinline__ void fast_load(const FastOperand& o, uint32_t i2, uin
     for (int j = 0; j < VEC; ++j) v[j] = o.imm;
     return;
   }
-  int64_t off = (int64_t)i2 * o.s2 + (int64_t)i1 * o.s1;
+  const int64_t off = (int64_t)(int32_t)i2 * (int64_t)o.s2 + (int64_t)(int32_t)i1 * (int64_t)o.s1;
   if (o.kind == K_F32) {
     const float* p = (const float*)o.ptr + off;
     if (o.s0 == 0) {

@@ -11,6 +11,7 @@
 // Both are two-pass when split (partials -> same kernel again), so results are deterministic.
 // Everything else (other dtypes, scattered axes, arg-reductions) takes the generic kernel.
 #include <algorithm>
+#include <cstdlib>
 #include <limits>
 
 #include "ew_ops.cuh"
@@ -65,6 +66,26 @@ __device__ __forceinline__ void load_apply(const RedParams& p, uint32_t i2, uint
     r[j] = apply<OP, float>(v[0][j], NIN > 1 ? v[1][j] : 0.f, NIN > 2 ? v[2][j] : 0.f, p.aux);
 }
 
+// U items: all loads first, then the elementwise functor (keeps U*NIN loads in flight per thread)
+template <int OP, int NIN, int VEC, int U>
+__device__ __forceinline__ void load_then_apply(const RedParams& p, const uint32_t (&i2)[U], const uint32_t (&i1)[U],
+                                                const uint32_t (&col)[U], const bool (&ok)[U], float (&r)[U][VEC]) {
+  float v[U][3][VEC];
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (ok[u]) {
+#pragma unroll
+      for (int k = 0; k < NIN; ++k) fast_load<VEC>(p.in[k], i2[u], i1[u], col[u], v[u][k]);
+    }
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (ok[u]) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j)
+        r[u][j] = apply<OP, float>(v[u][0][j], NIN > 1 ? v[u][1][j] : 0.f, NIN > 2 ? v[u][2][j] : 0.f, p.aux);
+    }
+}
+
 __device__ __forceinline__ void final_store(const RedParams& p, float* where, float v) {
   if (p.divisor > 0.f) v = __fdiv_rn(v, p.divisor);
   if (p.accumulate) v = __fadd_rn(*where, v);
@@ -110,9 +131,11 @@ __global__ void __launch_bounds__(256) red_row_cta(const RedParams p) {
   for (int j = 0; j < VEC; ++j) acc[j] = red_identity<RED>();
   for (uint32_t c = start + threadIdx.x; c < end; c += 256 * U) {
     float r[U][VEC];
+    uint32_t a2[U], a1[U], cc[U];
+    bool ok[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (c + u * 256 < end) load_apply<OP, NIN, VEC>(p, i2, i1, (c + u * 256) * VEC, r[u]);
+    for (int u = 0; u < U; ++u) { a2[u] = i2; a1[u] = i1; cc[u] = (c + u * 256) * VEC; ok[u] = c + u * 256 < end; }
+    load_then_apply<OP, NIN, VEC, U>(p, a2, a1, cc, ok, r);
 #pragma unroll
     for (int u = 0; u < U; ++u)
       if (c + u * 256 < end) {
@@ -152,9 +175,11 @@ __global__ void __launch_bounds__(256) red_col(const RedParams p) {
   if (active) {
     for (uint32_t r = r0 + ty; r < r1; r += 8 * U) {
       float v[U][VEC];
+      uint32_t a2[U], a1[U], cc[U];
+      bool ok[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (r + u * 8 < r1) load_apply<OP, NIN, VEC>(p, o2, r + u * 8, col, v[u]);
+      for (int u = 0; u < U; ++u) { a2[u] = o2; a1[u] = r + u * 8; cc[u] = col; ok[u] = r + u * 8 < r1; }
+      load_then_apply<OP, NIN, VEC, U>(p, a2, a1, cc, ok, v);
 #pragma unroll
       for (int u = 0; u < U; ++u)
         if (r + u * 8 < r1) {
@@ -310,7 +335,7 @@ static bool aligned16(const void* p, size_t a) { return ((uintptr_t)p % a) == 0;
 #define MDB_FUSED_RED_OPS(X)                                                                    \
   X(MDB_OP_COPY, 1) X(MDB_OP_NEG, 1) X(MDB_OP_MUL, 2) X(MDB_OP_DIV, 2) X(MDB_OP_SIN_BWD, 2)     \
   X(MDB_OP_COS_BWD, 2) X(MDB_OP_EXP_BWD, 2) X(MDB_OP_LOG_BWD, 2) X(MDB_OP_RELU_MASK_BWD, 2)     \
-  X(MDB_OP_POW_BWD, 3) X(MDB_OP_DIV_BWD_Y, 3)
+  X(MDB_OP_POW_BWD, 3) X(MDB_OP_DIV_BWD_Y, 3) X(MDB_OP_POW_BWD_LIN, 3)
 
 template <int OP, int NIN, int RED>
 static int launch_fast_red(const RedPlan& pl, RedParams p, int vec, float* out, bool accumulate,
@@ -330,8 +355,9 @@ static int launch_fast_red(const RedPlan& pl, RedParams p, int vec, float* out, 
       return 0;
     }
     // long rows: split so that >= ~4 CTAs per SM exist, each split >= 4096 work items
-    int64_t want = ((int64_t)g_sm_count * 4 + rows - 1) / rows;
-    int64_t maxsplit = std::max<int64_t>(1, L / 4096);
+    // many short CTAs (like the 8192-row axis=1 case, 0.94 of peak) beat few long ones
+    int64_t want = ((int64_t)g_sm_count * 32 + rows - 1) / rows;
+    int64_t maxsplit = std::max<int64_t>(1, L / 2048);
     uint32_t nsplit = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(std::min(want, maxsplit), 65535));
     uint32_t seg = (L + nsplit - 1) / nsplit;
     nsplit = (L + seg - 1) / seg;
@@ -350,10 +376,15 @@ static int launch_fast_red(const RedPlan& pl, RedParams p, int vec, float* out, 
     if (nsplit > 1) {  // second pass over the [rows, nsplit] partials
       RedParams q = p;
       q.in[0].ptr = tmp.ptr; q.in[0].kind = K_F32; q.in[0].s0 = 1;
-      q.in[0].s1 = nsplit; q.in[0].s2 = (int64_t)nsplit * pl.d1;
+      q.in[0].s1 = (int32_t)nsplit; q.in[0].s2 = (int32_t)((int64_t)nsplit * pl.d1);
       q.L = nsplit; q.seg = nsplit; q.nsplit = 1; q.dst = out; q.to_partial = 0;
-      int grid2 = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)g_sm_count * 16);
-      red_row_warp<MDB_OP_COPY, 1, RED, 1><<<grid2, 256, 0, g_stream>>>(q);
+      q.rows = (uint32_t)rows;
+      if (nsplit <= 256) {          // a warp per row of partials
+        int grid2 = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)g_sm_count * 16);
+        red_row_warp<MDB_OP_COPY, 1, RED, 1><<<grid2, 256, 0, g_stream>>>(q);
+      } else {                      // long rows of partials (full reductions): a CTA per row
+        red_row_cta<MDB_OP_COPY, 1, RED, 1><<<dim3((unsigned)rows, 1), 256, 0, g_stream>>>(q);
+      }
       MDB_CHECK_LAUNCH();
     }
     return 0;
@@ -363,9 +394,10 @@ static int launch_fast_red(const RedPlan& pl, RedParams p, int vec, float* out, 
   p.L = (uint32_t)R; p.I = (uint32_t)I; p.os2 = pl.ostr[0];
   const int tile = 32 * vec;
   const int64_t gx = (I + tile - 1) / tile;
-  int64_t want = ((int64_t)g_sm_count * 4 + gx * O2 - 1) / (gx * O2);
+  int64_t want = ((int64_t)g_sm_count * 8 + gx * O2 - 1) / (gx * O2);
   int64_t maxsplit = std::max<int64_t>(1, R / 64);
   uint32_t nsplit = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(std::min(want, maxsplit), 1024));
+  if ((int64_t)nsplit * I * O2 >= (int64_t(1) << 31)) nsplit = 1;
   uint32_t seg = (uint32_t)((R + nsplit - 1) / nsplit);
   nsplit = (uint32_t)((R + seg - 1) / seg);
   p.seg = seg; p.nsplit = nsplit;
@@ -383,7 +415,7 @@ static int launch_fast_red(const RedPlan& pl, RedParams p, int vec, float* out, 
   if (nsplit > 1) {
     RedParams q = p;
     q.in[0].ptr = tmp.ptr; q.in[0].kind = K_F32; q.in[0].s0 = 1;
-    q.in[0].s1 = I; q.in[0].s2 = (int64_t)nsplit * I;
+    q.in[0].s1 = (int32_t)I; q.in[0].s2 = (int32_t)((int64_t)nsplit * I);
     q.L = nsplit; q.seg = nsplit; q.nsplit = 1; q.dst = out; q.to_partial = 0;
     const bool v4 = (vec == 4);  // partial rows are 16B aligned iff I % 4 == 0 (true when vec == 4)
     dim3 grid2((unsigned)gx, 1, (unsigned)O2);
@@ -451,6 +483,12 @@ static int reduce_driver(int op, int red, const mdb_array* out, int n_in, const 
   fast_ok = fast_ok && n_red > 0 && n_red < (int64_t(1) << 31) && n_out < (int64_t(1) << 31) &&
             plan_fast(nd, full, redax, n_in, istr, ostr, &pl);
   if (fast_ok && pl.pattern == 1 && pl.d2 > 65535) fast_ok = false;
+  if (fast_ok) {                                   // kernel operands carry 32-bit strides
+    const int64_t lim = int64_t(1) << 31;
+    for (int k = 0; k < n_in; ++k)
+      for (int j = 0; j < 3; ++j) fast_ok = fast_ok && pl.istr[k][j] < lim && pl.istr[k][j] > -lim;
+    fast_ok = fast_ok && pl.d2 * pl.d1 * 1024 < lim;   // room for the [rows, nsplit] partials indexing
+  }
   if (fast_ok) {
     RedParams p;
     p.aux = 0.f;
@@ -459,7 +497,7 @@ static int reduce_driver(int op, int red, const mdb_array* out, int n_in, const 
       FastOperand& o = p.in[k];
       o.ptr = in[k].ptr; o.imm = (float)in[k].imm;
       o.kind = in[k].ptr == nullptr ? K_IMM : (in[k].dtype == MDB_F32 ? K_F32 : K_U8);
-      o.s2 = pl.istr[k][0]; o.s1 = pl.istr[k][1]; o.s0 = (int)pl.istr[k][2];
+      o.s2 = (int32_t)pl.istr[k][0]; o.s1 = (int32_t)pl.istr[k][1]; o.s0 = (int)pl.istr[k][2];
       if (o.kind != K_IMM && o.s0 == 1) {
         size_t esz = o.kind == K_F32 ? 4 : 1;
         v4 = v4 && aligned16(o.ptr, 4 * esz) && o.s1 % 4 == 0 && o.s2 % 4 == 0;
@@ -468,6 +506,7 @@ static int reduce_driver(int op, int red, const mdb_array* out, int n_in, const 
     if (op == MDB_OP_POW_BWD) {
       MDB_REQUIRE(in[2].ptr == nullptr, "POW_BWD needs an immediate exponent");
       p.aux = (float)(in[2].imm - 1.0);
+      if (in[2].imm == 2.0) op = MDB_OP_POW_BWD_LIN;
     }
     if (pl.pattern == 1) v4 = v4 && aligned16(out->ptr, 16) && pl.ostr[0] % 4 == 0;
     const int vec = v4 ? 4 : 1;

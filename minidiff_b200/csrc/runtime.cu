@@ -1,6 +1,7 @@
 // Runtime of libminidiff_b200: device/stream ownership, caching allocator, copies, events.
 // Stands behind array creation / as_numpy / finalizers of the backend boundary.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -51,12 +52,23 @@ struct Allocator {
   }
   int alloc(size_t bytes, void** out) {
     size_t r = round(bytes);
-    auto it = free_lists.find(r);
-    if (it != free_lists.end() && !it->second.empty()) {
+    // exact class first, then the smallest cached block within 1.5x (large blocks only): a
+    // cudaMalloc is a device-wide synchronisation and costs milliseconds at GB sizes
+    auto it = free_lists.lower_bound(r);
+    while (it != free_lists.end() && it->second.empty()) ++it;
+    if (it != free_lists.end() && (it->first == r || (r >= (8u << 20) && it->first <= r + r / 2))) {
+      r = it->first;
       *out = it->second.back();
       it->second.pop_back();
       cached -= r;
     } else {
+      static const bool trace = getenv("MDB_ALLOC_TRACE") != nullptr;
+      if (trace) {
+        size_t nfree = 0;
+        for (auto& kv : free_lists) nfree += kv.second.size();
+        fprintf(stderr, "[mdb alloc miss] %.1f MB (request %.1f MB), cached blocks %zu / %.1f MB\n", r / 1e6,
+                bytes / 1e6, nfree, cached / 1e6);
+      }
       cudaError_t e = cudaMalloc(out, r);
       if (e != cudaSuccess) {
         cudaGetLastError();
