@@ -147,7 +147,9 @@ int mdb_elementwise_reduce(int op, const mdb_array* out, int n_in, const mdb_arr
  * tcgen05 tensor cores when shapes allow, else an fp32 CUDA-core kernel.
  * C = A@B (accumulate=0) or C += A@B (accumulate=1, the in-place form of topology.py:101-104). */
 int mdb_gemm(const mdb_array* c, const mdb_array* a, const mdb_array* b, int accumulate);
-int mdb_gemm_config(int force_path);              /* 0 auto, 1 SIMT only, 2 tcgen05 only (tests)  */
+int mdb_gemm_tune(int flags);                     /* kernel tuning switches for A/B measurements   */
+int mdb_gemm_config(int force_path);              /* 0 auto, 1 CUDA-core kernel only, 2 tensor-core
+                                                     kernel only (tests) */
 
 /* integer-array indexing (getitem / `a[key] = v` / index_add with array keys:
  * backend/numpy.py:73-75,105; tensor.py:376-379) over the leading axis:

@@ -86,6 +86,7 @@ _SIGS = {
     "mdb_elementwise_reduce": (C.c_int, [C.c_int, _A, C.c_int, _A, C.c_int]),
     "mdb_gemm": (C.c_int, [_A, _A, _A, C.c_int]),
     "mdb_gemm_config": (C.c_int, [C.c_int]),
+    "mdb_gemm_tune": (C.c_int, [C.c_int]),
     "mdb_gather_rows": (C.c_int, [_A, _A, _A]),
     "mdb_scatter_rows": (C.c_int, [_A, _A, _A, C.c_int]),
     "mdb_random": (C.c_int, [_A, C.c_int, C.c_uint64, C.c_uint64]),

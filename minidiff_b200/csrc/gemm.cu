@@ -7,6 +7,7 @@ namespace mdb {
 
 int gemm_tcgen05(const mdb_array* c, const mdb_array* a, const mdb_array* b, int accumulate);
 static int g_force_path = 0;
+extern int g_gemm_flags;
 
 // 64x64 output tile per CTA, K step 16, 4x4 micro-tile per thread; operands addressed through
 // (row, col) element strides so NN / NT / TN views need no copies.
@@ -89,6 +90,11 @@ extern "C" {
 int mdb_gemm_config(int force_path) {
   MDB_REQUIRE(force_path >= 0 && force_path <= 2, "force_path must be 0, 1 or 2");
   g_force_path = force_path;
+  return 0;
+}
+
+int mdb_gemm_tune(int flags) {
+  g_gemm_flags = flags;
   return 0;
 }
 

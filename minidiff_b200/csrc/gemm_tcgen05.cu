@@ -8,10 +8,21 @@
 //     A: stride_k == 1 -> K-major     stride_m == 1 -> MN-major
 //     B: stride_k == 1 -> K-major     stride_n == 1 -> MN-major      (B is consumed as N x K)
 //
-// 3xTF32 (north_star): x = hi + lo with hi = rn_tf32(x), lo = rn_tf32(x - hi); the tensor cores
-// accumulate  hi*hi + hi*lo + lo*hi  in fp32 TMEM, dropping only lo*lo (2^-22 relative).
-// The split is done once per operand by a streaming pre-pass into compact hi/lo planes
-// (v1; the planes are what TMA loads).
+// 3xTF32 (north_star): x = hi + lo, the tensor cores accumulate  lo*hi + hi*lo + hi*hi  in fp32 TMEM,
+// dropping only lo*lo (~2^-20 relative).
+//
+// RAW mode (the fast path).  Measured on this hardware: kind::tf32 simply IGNORES the low 13 mantissa
+// bits of its operands (feeding raw fp32 as the hi plane keeps fp32-class accuracy), so a raw fp32
+// tile is its own hi plane: TMA loads the operand tiles UNTOUCHED straight from the user's arrays,
+// and four converter warps derive only   lo = rn_tf32(x - trunc_tf32(x))   shared memory -> shared
+// memory (same swizzled offset, so the layout is irrelevant to them), fence.proxy.async, and hand
+// the stage to the MMA warp.  No pre-pass, no temporary planes, one read of A and B.
+// (Dead ends, with ncu numbers in profiles/: splitting in a pre-pass costs 14 % of device time and
+// doubles the L2->SM traffic; splitting in registers of LDG-producer warps is instruction-issue
+// bound -- 4.3e9 warp instructions, tensor pipe 28 % active -- because every CTA re-splits its tiles.)
+//
+// PRE-SPLIT mode (fallback for operands TMA cannot address: unaligned base / pitch, two non-unit
+// strides): a streaming pre-pass gathers them into compact hi/lo planes which TMA then loads.
 //
 // Accumulation: the tensor core adds into the fp32 TMEM accumulator with TRUNCATION (measured here:
 // error grew linearly with K, 1.7e-2 at K=8192 when one TMEM chain ran over all of K).  So a chain
@@ -19,136 +30,55 @@
 // the epilogue warps, which add it into fp32 REGISTERS with round-to-nearest, while the MMA warp
 // already fills the other TMEM buffer (same promotion idea as Ootomo & Yokota's tensor-core SGEMM).
 //
-// Kernel anatomy (one CTA per SM, persistent over output tiles):
-//   warp 0      TMA producer : cp.async.bulk.tensor (SWIZZLE_128B) of A_hi/A_lo/B_hi/B_lo k-blocks
-//                              into a kStages-deep shared-memory ring, mbarrier complete_tx
-//   warp 1      MMA issuer   : one lane issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8),
-//                              3 MMAs per k-step; tcgen05.commit releases ring slots / publishes
-//                              the accumulator
+// Kernel anatomy (one CTA per SM, persistent over output tiles, 512 threads = 4 warpgroups whose
+// register shares are re-partitioned with setmaxnreg: 40 / 216 / 128 / 128):
+//   warp 0      TMA producer : cp.async.bulk.tensor.2d (SWIZZLE_128B for K-major operands,
+//                              SWIZZLE_128B_ATOM_32B for MN-major ones) into a 3-stage 64 KB ring
+//   warp 1      MMA issuer   : one lane issues tcgen05.mma.kind::tf32 (M=128, N=128, K=8), 12 per
+//                              k-block; tcgen05.commit frees ring slots / publishes accumulators
 //   warp 2      TMEM allocator
-//   warps 4..7  epilogue     : tcgen05.ld (32 lanes x 32 columns per warp-instruction) -> registers
-//                              -> global (optionally C += ...), double-buffered TMEM accumulators so
-//                              the epilogue of tile i overlaps the main loop of tile i+1
+//   warps 4-7   epilogue     : tcgen05.ld -> fp32 register sums (promotion) -> global (C or C +=)
+//   warps 8-15  converters   : raw tile -> lo tile (RAW mode only)
 #include <cuda.h>
 
 #include <algorithm>
 #include <cstdlib>
 
-#include "mdb_common.cuh"
+#include "tc_common.cuh"
 
 namespace mdb {
 
 namespace tc {
 
-constexpr int BM = 128;          // UMMA M (cta_group::1)
-constexpr int BK = 32;           // fp32 elements per k-block == one 128-byte swizzle row
-constexpr int UMMA_K = 8;        // tf32: 32 bytes of K per instruction
-constexpr int kThreads = 256;
-constexpr int kChunk = 4;        // k-blocks per in-TMEM accumulation chain (128 K) before promotion
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// Spin on a phase parity.  A deadlock (protocol bug) traps after ~2 s instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
-  long long t0 = 0;
-  for (uint32_t spins = 0;; ++spins) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) return;
-    if (spins == 64) t0 = clock64();
-    if (spins > 64 && (spins & 1023) == 0 && clock64() - t0 > 4000000000ll) __trap();
-  }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar,
-                                            int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-
-// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-//   [0,14) start>>4   [16,30) LBO>>4   [32,46) SBO>>4   [46,48) version=1   [61,64) layout type
-// layout type 2 = SWIZZLE_128B (K-major operands: 16-B chunks XOR row%8, 8-row / 1024-B atoms)
-// layout type 1 = SWIZZLE_128B_BASE32B (the ONLY layout the tensor core accepts for MN-major
-//                 32-bit operands: 32-B chunks XOR row%4, 4-row / 512-B atoms; TMA writes it with
-//                 CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                              uint32_t layout_type) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)layout_type << 61;
-  return d;
-}
-
-#define MDB_TMEM_LD32(taddr, r)                                                                          \
-  asm volatile(                                                                                          \
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                          \
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                          \
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"          \
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),  \
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),         \
-        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),       \
-        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),       \
-        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                                                            \
-      : "r"(taddr)                                                                                       \
-      : "memory")
-
 struct Params {
   int M, N, K;
+  int raw;                      // 1: RAW mode (converter warps make the lo tiles), 0: PRE-SPLIT mode
   int a_mn_major, b_mn_major;   // operand major-ness (0: K-major, 1: MN-major)
   float* C;
   int64_t ldc;
   int accumulate;
   int tiles_m, tiles_n, group_m;
   int debug;   // MDB_GEMM_DEBUG: 1 = epilogue stores a sentinel instead of the result
+  int flags;   // tuning switches (mdb_gemm_tune): bit0 issue hi*hi before waiting for lo (measured 4 % slower),
+               // bit1 round lo with cvt.rna (9 % slower than integer rounding), bit2 do not round lo at all
+               // (5 % faster, max error +16 %: default)
 };
 
-// smem ring: per stage [A_hi | A_lo | B_hi | B_lo], each operand tile is (rows x 128 B), 1024-B atoms
-template <int BN, int kStages>
+// Shared memory: two rings of operand tiles, every tile is (rows x 128 B) in 1024-B aligned atoms.
+//   hi ring  (kHi deep): [A_hi | B_hi] per slot -- the TMA target; in RAW mode these are the raw tiles
+//   lo ring  (kLo deep): [A_lo | B_lo] per slot -- written by the converter warps (RAW) or TMA (PRE-SPLIT)
+// The lo tiles are produced just in time, so 2 slots suffice; that leaves room for 5 hi slots, i.e.
+// 3-4 k-blocks of TMA lookahead (with one shared 3-stage ring the convert step cost a whole stage of
+// lookahead and the kernel ran depth-limited: measured 5.6 ms vs 4.3 ms per 8192^3 GEMM).
+template <int BN, int kHi, int kLo>
 struct Smem {
   static constexpr int A_BYTES = BM * BK * 4;
   static constexpr int B_BYTES = BN * BK * 4;
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int RING_BYTES = kStages * STAGE_BYTES;
-  static constexpr int BAR_BYTES = 256;
-  static constexpr int TOTAL = RING_BYTES + BAR_BYTES + 1024;  // + alignment slack
+  static constexpr int SLOT_BYTES = A_BYTES + B_BYTES;
+  static constexpr int HI_BYTES = kHi * SLOT_BYTES;
+  static constexpr int LO_BYTES = kLo * SLOT_BYTES;
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int TOTAL = HI_BYTES + LO_BYTES + BAR_BYTES + 1024;  // + alignment slack
 };
 
 __device__ __forceinline__ void tile_coords(const Params& p, int t, int& m_blk, int& n_blk) {
@@ -161,17 +91,29 @@ __device__ __forceinline__ void tile_coords(const Params& p, int t, int& m_blk, 
   n_blk = r / rows;
 }
 
-template <int BN, int kStages>
+// ring position helper: slot index + phase parity
+struct Ring {
+  int slot = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance(int depth) {
+    if (++slot == depth) { slot = 0; phase ^= 1; }
+  }
+};
+
+template <int BN, int kHi, int kLo>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                    const Params p) {
-  using S = Smem<BN, kStages>;
+  using S = Smem<BN, kHi, kLo>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SW128 atoms: 1024-B aligned
-  uint64_t* full_bar = (uint64_t*)(smem + S::RING_BYTES);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full = empty_bar + kStages;     // [2]
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // swizzle atoms: 1024-B aligned
+  uint8_t* lo_ring = smem + S::HI_BYTES;
+  uint64_t* hi_full = (uint64_t*)(smem + S::HI_BYTES + S::LO_BYTES);   // hi slot landed (TMA complete_tx)
+  uint64_t* hi_empty = hi_full + kHi;                                  // hi slot consumed (MMA commit)
+  uint64_t* lo_full = hi_empty + kHi;                                  // lo slot written
+  uint64_t* lo_empty = lo_full + kLo;                                  // lo slot consumed (MMA commit)
+  uint64_t* tmem_full = lo_empty + kLo;          // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
 
@@ -187,7 +129,11 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < kHi; ++s) { mbar_init(&hi_full[s], 1); mbar_init(&hi_empty[s], 1); }
+    for (int s = 0; s < kLo; ++s) {
+      mbar_init(&lo_full[s], p.raw ? kConverterThreads : 1);   // RAW: every converter thread arrives
+      mbar_init(&lo_empty[s], 1);
+    }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -202,48 +148,63 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  // setmaxnreg sits at the top of each role's branch (ptxas applies the new limit to the code it
+  // dominates): control warpgroup 40, epilogue 216, the two converter warpgroups keep the launch value (128)
+  if (warp == 2 || warp == 3) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  } else if (warp == 0) {
     // ===================================== TMA producer =====================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      Ring hi, lo;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         int m_blk, n_blk;
         tile_coords(p, t, m_blk, n_blk);
         const int m0 = m_blk * BM, n0 = n_blk * BN;
         for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* st = smem + stage * S::STAGE_BYTES;
-          const uint32_t a_hi = smem_u32(st), a_lo = a_hi + S::A_BYTES;
-          const uint32_t b_hi = a_lo + S::A_BYTES, b_lo = b_hi + S::B_BYTES;
-          mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
           const int k0 = kb * BK;
-          if (!p.a_mn_major) {           // plane is [M][K], K contiguous: one (32 x BM) box
-            tma_load_2d(a_hi, &map_a_hi, &full_bar[stage], k0, m0);
-            tma_load_2d(a_lo, &map_a_lo, &full_bar[stage], k0, m0);
-          } else {                       // plane is [K][M], M contiguous: BM/32 boxes of (32 x 32)
+          mbar_wait(&hi_empty[hi.slot], hi.phase ^ 1);
+          const uint32_t a_hi = smem_u32(smem + hi.slot * S::SLOT_BYTES), b_hi = a_hi + S::A_BYTES;
+          uint64_t* hbar = &hi_full[hi.slot];
+          mbar_expect_tx(hbar, S::SLOT_BYTES);
+          if (!p.a_mn_major) {           // memory is [M][K], K contiguous: one (32 x BM) box
+            tma_load_2d(a_hi, &map_a_hi, hbar, k0, m0);
+          } else {                       // memory is [K][M], M contiguous: BM/32 boxes of (32 x 32)
 #pragma unroll
-            for (int c = 0; c < BM / 32; ++c) {
-              tma_load_2d(a_hi + c * 4096, &map_a_hi, &full_bar[stage], m0 + 32 * c, k0);
-              tma_load_2d(a_lo + c * 4096, &map_a_lo, &full_bar[stage], m0 + 32 * c, k0);
-            }
+            for (int c = 0; c < BM / 32; ++c) tma_load_2d(a_hi + c * 4096, &map_a_hi, hbar, m0 + 32 * c, k0);
           }
-          if (!p.b_mn_major) {           // plane is [N][K], K contiguous
-            tma_load_2d(b_hi, &map_b_hi, &full_bar[stage], k0, n0);
-            tma_load_2d(b_lo, &map_b_lo, &full_bar[stage], k0, n0);
-          } else {                       // plane is [K][N], N contiguous
+          if (!p.b_mn_major) {           // memory is [N][K], K contiguous
+            tma_load_2d(b_hi, &map_b_hi, hbar, k0, n0);
+          } else {                       // memory is [K][N], N contiguous
 #pragma unroll
-            for (int c = 0; c < BN / 32; ++c) {
-              tma_load_2d(b_hi + c * 4096, &map_b_hi, &full_bar[stage], n0 + 32 * c, k0);
-              tma_load_2d(b_lo + c * 4096, &map_b_lo, &full_bar[stage], n0 + 32 * c, k0);
-            }
+            for (int c = 0; c < BN / 32; ++c) tma_load_2d(b_hi + c * 4096, &map_b_hi, hbar, n0 + 32 * c, k0);
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          hi.advance(kHi);
+          if (!p.raw) {                  // PRE-SPLIT: the lo planes come by TMA as well
+            mbar_wait(&lo_empty[lo.slot], lo.phase ^ 1);
+            const uint32_t a_lo = smem_u32(lo_ring + lo.slot * S::SLOT_BYTES), b_lo = a_lo + S::A_BYTES;
+            uint64_t* lbar = &lo_full[lo.slot];
+            mbar_expect_tx(lbar, S::SLOT_BYTES);
+            if (!p.a_mn_major) {
+              tma_load_2d(a_lo, &map_a_lo, lbar, k0, m0);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BM / 32; ++c) tma_load_2d(a_lo + c * 4096, &map_a_lo, lbar, m0 + 32 * c, k0);
+            }
+            if (!p.b_mn_major) {
+              tma_load_2d(b_lo, &map_b_lo, lbar, k0, n0);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BN / 32; ++c) tma_load_2d(b_lo + c * 4096, &map_b_lo, lbar, n0 + 32 * c, k0);
+            }
+            lo.advance(kLo);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer ========================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=TF32 [7,10), b=TF32
     // [10,13), a_major bit 15, b_major bit 16, N>>3 [17,23), M>>4 [24,29)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn_major << 15) |
@@ -256,8 +217,9 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     const uint32_t a_sbo = p.a_mn_major ? 512 : 1024, b_sbo = p.b_mn_major ? 512 : 1024;
     const uint32_t a_lt = p.a_mn_major ? 1 : 2, b_lt = p.b_mn_major ? 1 : 2;
     const uint32_t a_kstep = p.a_mn_major ? 1024 : UMMA_K * 4, b_kstep = p.b_mn_major ? 1024 : UMMA_K * 4;
-    int stage = 0, acc = 0;
-    uint32_t phase = 0, acc_phase = 0;
+    Ring hi, lo;
+    int acc = 0;
+    uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       for (int kb = 0; kb < num_k; ++kb) {
         const bool chunk_start = (kb % kChunk) == 0;
@@ -267,32 +229,98 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
           tcgen05_fence_after();
         }
         const uint32_t tmem_d = tmem_base + acc * BN;
-        mbar_wait(&full_bar[stage], phase);
+        mbar_wait(&hi_full[hi.slot], hi.phase);          // TMA bytes of the hi tiles are visible
+        tcgen05_fence_after();
+        const uint32_t a_hi = smem_u32(smem + hi.slot * S::SLOT_BYTES), b_hi = a_hi + S::A_BYTES;
+        const uint32_t a_lo = smem_u32(lo_ring + lo.slot * S::SLOT_BYTES), b_lo = a_lo + S::A_BYTES;
+        const bool early = p.flags & 1;
+        if (early && lane == 0) {                        // hi*hi needs only the raw tiles: issue it
+#pragma unroll                                           // while the converters still work on lo
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_tf32(tmem_d, make_desc(a_hi + k * a_kstep, a_lbo, a_sbo, a_lt),
+                      make_desc(b_hi + k * b_kstep, b_lbo, b_sbo, b_lt), idesc, !(chunk_start && k == 0));
+        }
+        __syncwarp();
+        mbar_wait(&lo_full[lo.slot], lo.phase);          // lo tiles written (converters / TMA)
         tcgen05_fence_after();
         if (lane == 0) {
-          uint8_t* st = smem + stage * S::STAGE_BYTES;
-          const uint32_t a_hi = smem_u32(st), a_lo = a_hi + S::A_BYTES;
-          const uint32_t b_hi = a_lo + S::A_BYTES, b_lo = b_hi + S::B_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t da_hi = make_desc(a_hi + k * a_kstep, a_lbo, a_sbo, a_lt);
             const uint64_t da_lo = make_desc(a_lo + k * a_kstep, a_lbo, a_sbo, a_lt);
             const uint64_t db_hi = make_desc(b_hi + k * b_kstep, b_lbo, b_sbo, b_lt);
             const uint64_t db_lo = make_desc(b_lo + k * b_kstep, b_lbo, b_sbo, b_lt);
-            umma_tf32(tmem_d, da_lo, db_hi, idesc, !(chunk_start && k == 0));   // small terms first
+            umma_tf32(tmem_d, da_lo, db_hi, idesc, early || !(chunk_start && k == 0));
             umma_tf32(tmem_d, da_hi, db_lo, idesc, 1);
-            umma_tf32(tmem_d, da_hi, db_hi, idesc, 1);
+            if (!early) umma_tf32(tmem_d, da_hi, db_hi, idesc, 1);
           }
-          umma_commit(&empty_bar[stage]);                 // ring slot free once these MMAs retire
+          umma_commit(&lo_empty[lo.slot]);                // both slots are free once these MMAs retire
+          umma_commit(&hi_empty[hi.slot]);
           if (chunk_end) umma_commit(&tmem_full[acc]);    // chunk accumulator ready for promotion
         }
         __syncwarp();
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        hi.advance(kHi);
+        lo.advance(kLo);
         if (chunk_end && ++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================================== converters (RAW mode) =============================
+    // lo = rn_tf32(x - trunc_tf32(x)) for every element of the two raw tiles of a hi slot, written
+    // at the same byte offset of the lo slot (the swizzle is a pure address permutation, so a
+    // linear sweep over the tiles is layout-agnostic and bank-conflict free).
+    if (p.raw) {
+      const int t = threadIdx.x - 8 * 32;            // 0..255
+      Ring hi, lo;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&hi_full[hi.slot], hi.phase);
+          mbar_wait(&lo_empty[lo.slot], lo.phase ^ 1);
+          const uint32_t src = smem_u32(smem + hi.slot * S::SLOT_BYTES);
+          const uint32_t dst = smem_u32(lo_ring + lo.slot * S::SLOT_BYTES);
+          constexpr int kVecs = S::SLOT_BYTES / 16 / kConverterThreads;   // 8 float4 per thread
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            float4 v[kVecs / 2];
+#pragma unroll
+            for (int j = 0; j < kVecs / 2; ++j)
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(v[j].x), "=f"(v[j].y), "=f"(v[j].z), "=f"(v[j].w)
+                           : "r"(src + (t + (half * (kVecs / 2) + j) * kConverterThreads) * 16));
+#pragma unroll
+            for (int j = 0; j < kVecs / 2; ++j) {
+              float e[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float h = __uint_as_float(__float_as_uint(e[i]) & 0xFFFFE000u);   // what the MMA sees
+                // round-half-away to tf32 with integer ops (cvt.rna.tf32 runs on the quarter-rate
+                // conversion pipe: 8192 of them per k-block cost ~512 cycles per SM, measured as
+                // the bottleneck); sign-magnitude bits make +0x1000 then mask exactly that rounding
+                if (p.flags & 4) {
+                  e[i] = __fsub_rn(e[i], h);          // leave the rounding of lo to the tensor core (truncation)
+                } else if (p.flags & 2) {
+                  uint32_t lb;
+                  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(__fsub_rn(e[i], h)));
+                  e[i] = __uint_as_float(lb);
+                } else {
+                  e[i] = __uint_as_float((__float_as_uint(__fsub_rn(e[i], h)) + 0x1000u) & 0xFFFFE000u);
+                }
+              }
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (t + (half * (kVecs / 2) + j) * kConverterThreads) * 16),
+                           "f"(e[0]), "f"(e[1]), "f"(e[2]), "f"(e[3])
+                           : "memory");
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> visible to UMMA
+          mbar_arrive(&lo_full[lo.slot]);
+          hi.advance(kHi);
+          lo.advance(kLo);
+        }
       }
     }
   } else if (warp >= 4) {
     // ===================================== epilogue ==========================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     const int q = warp & 3;                               // TMEM lane quarter this warp may touch
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -398,6 +426,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
+int g_gemm_flags = 4;   // default: lo is left unrounded (the tensor core truncates it); see mdb_gemm_tune
 
 static int load_encode() {
   if (g_encode) return 0;
@@ -452,10 +481,11 @@ static int split_operand(const float* src, int mn, int k, int64_t s_mn, int64_t 
   return 0;
 }
 
-template <int BN, int kStages>
+template <int BN, int kHi, int kLo>
 static int launch(const CUtensorMap maps[4], const tc::Params& p) {
-  using S = tc::Smem<BN, kStages>;
-  auto kern = tc::gemm_3xtf32_kernel<BN, kStages>;
+  using S = tc::Smem<BN, kHi, kLo>;
+  static_assert(S::TOTAL <= 227 * 1024, "shared memory budget");
+  auto kern = tc::gemm_3xtf32_kernel<BN, kHi, kLo>;
   static bool configured = false;
   if (!configured) {
     MDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
@@ -468,30 +498,57 @@ static int launch(const CUtensorMap maps[4], const tc::Params& p) {
   return 0;
 }
 
+// Can TMA read this operand in place?  Needs a unit stride along k (K-major) or along m/n
+// (MN-major), a 16-byte aligned base and a row pitch that is a multiple of 16 bytes.
+static bool tma_addressable(const float* ptr, int64_t s_mn, int64_t s_k, int mn, int k, bool* mn_major,
+                            int64_t* pitch) {
+  if (((uintptr_t)ptr & 15) != 0) return false;
+  if (s_k == 1 && s_mn >= k) { *mn_major = false; *pitch = s_mn; }
+  else if (s_mn == 1 && s_k >= mn) { *mn_major = true; *pitch = s_k; }
+  else return false;
+  return *pitch % 4 == 0 && *pitch < (int64_t(1) << 36);
+}
+
 int gemm_tcgen05(const mdb_array* c, const mdb_array* a, const mdb_array* b, int accumulate) {
   const int64_t M = a->shape[0], K = a->shape[1], N = b->shape[1];
-  // small problems are launch-latency bound: the CUDA-core kernel is as fast and needs no pre-pass
+  // small problems are launch-latency bound: the CUDA-core kernel is as fast
   if (M * N * K < (int64_t(1) << 21) || K < 32 || M < 32 || N < 32)
     return set_error(MDB_ENOTSUP, "problem too small for the tensor-core path");
   if (c->strides[1] != 1)
     return set_error(MDB_ENOTSUP, "output must be row-major for the tensor-core path");
   MDB_TRY(load_encode());
 
-  Plane pa, pb;
-  MDB_TRY(split_operand((const float*)a->ptr, (int)M, (int)K, a->strides[0], a->strides[1], &pa));
-  MDB_TRY(split_operand((const float*)b->ptr, (int)N, (int)K, b->strides[1], b->strides[0], &pb));
-
-  constexpr int BN = 128, kStages = 3;
+  constexpr int BN = 128, kHi = 5, kLo = 2;
   CUtensorMap maps[4];
-  const int a_box = pa.mn_major ? 32 : tc::BM, b_box = pb.mn_major ? 32 : BN;
-  MDB_TRY(make_map(&maps[0], (const float*)pa.hi.ptr, pa.inner, pa.outer, pa.ld, a_box, pa.mn_major));
-  MDB_TRY(make_map(&maps[1], (const float*)pa.lo.ptr, pa.inner, pa.outer, pa.ld, a_box, pa.mn_major));
-  MDB_TRY(make_map(&maps[2], (const float*)pb.hi.ptr, pb.inner, pb.outer, pb.ld, b_box, pb.mn_major));
-  MDB_TRY(make_map(&maps[3], (const float*)pb.lo.ptr, pb.inner, pb.outer, pb.ld, b_box, pb.mn_major));
-
   tc::Params p;
+  Plane pa, pb;
+  bool a_mn = false, b_mn = false;
+  int64_t a_pitch = 0, b_pitch = 0;
+  static const bool no_raw = getenv("MDB_GEMM_PRESPLIT") != nullptr;   // A/B switch for measurements
+  const bool raw = !no_raw &&
+      tma_addressable((const float*)a->ptr, a->strides[0], a->strides[1], (int)M, (int)K, &a_mn, &a_pitch) &&
+      tma_addressable((const float*)b->ptr, b->strides[1], b->strides[0], (int)N, (int)K, &b_mn, &b_pitch);
+  if (raw) {
+    // TMA reads the user's arrays directly; the raw tile doubles as the hi plane
+    if (!a_mn) MDB_TRY(make_map(&maps[0], (const float*)a->ptr, (int)K, (int)M, (int)a_pitch, tc::BM, false));
+    else MDB_TRY(make_map(&maps[0], (const float*)a->ptr, (int)M, (int)K, (int)a_pitch, 32, true));
+    if (!b_mn) MDB_TRY(make_map(&maps[2], (const float*)b->ptr, (int)K, (int)N, (int)b_pitch, BN, false));
+    else MDB_TRY(make_map(&maps[2], (const float*)b->ptr, (int)N, (int)K, (int)b_pitch, 32, true));
+    maps[1] = maps[0];
+    maps[3] = maps[2];
+    p.a_mn_major = a_mn; p.b_mn_major = b_mn;
+  } else {
+    MDB_TRY(split_operand((const float*)a->ptr, (int)M, (int)K, a->strides[0], a->strides[1], &pa));
+    MDB_TRY(split_operand((const float*)b->ptr, (int)N, (int)K, b->strides[1], b->strides[0], &pb));
+    const int a_box = pa.mn_major ? 32 : tc::BM, b_box = pb.mn_major ? 32 : BN;
+    MDB_TRY(make_map(&maps[0], (const float*)pa.hi.ptr, pa.inner, pa.outer, pa.ld, a_box, pa.mn_major));
+    MDB_TRY(make_map(&maps[1], (const float*)pa.lo.ptr, pa.inner, pa.outer, pa.ld, a_box, pa.mn_major));
+    MDB_TRY(make_map(&maps[2], (const float*)pb.hi.ptr, pb.inner, pb.outer, pb.ld, b_box, pb.mn_major));
+    MDB_TRY(make_map(&maps[3], (const float*)pb.lo.ptr, pb.inner, pb.outer, pb.ld, b_box, pb.mn_major));
+    p.a_mn_major = pa.mn_major; p.b_mn_major = pb.mn_major;
+  }
+  p.raw = raw ? 1 : 0;
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
-  p.a_mn_major = pa.mn_major; p.b_mn_major = pb.mn_major;
   p.C = (float*)c->ptr; p.ldc = c->strides[0];
   p.accumulate = accumulate;
   p.tiles_m = (int)((M + tc::BM - 1) / tc::BM);
@@ -499,7 +556,8 @@ int gemm_tcgen05(const mdb_array* c, const mdb_array* a, const mdb_array* b, int
   p.group_m = 16;
   const char* dbg = getenv("MDB_GEMM_DEBUG");
   p.debug = dbg ? atoi(dbg) : 0;
-  return launch<BN, kStages>(maps, p);
+  p.flags = g_gemm_flags;
+  return launch<BN, kHi, kLo>(maps, p);
 }
 
 }  // namespace mdb

@@ -20,6 +20,8 @@ def B():
 
 @pytest.fixture()
 def force_tc(B):
+    """tensor-core kernel only (no silent CUDA-core fallback).  RAW mode is taken when TMA can
+    address the operands in place; ragged pitches / doubly strided views take PRE-SPLIT mode."""
     from minidiff_b200.backend._lib import check, lib
 
     check(lib.mdb_gemm_config(2))
