@@ -50,17 +50,24 @@ def load_peaks():
 # clocks sampled during the timed region
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index=0):
         self.gpu, self.proc, self.lines = gpu_index, None, []
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -69,7 +76,7 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -80,7 +87,13 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
-        for ln in self.lines:
+        lines = self.lines
+        if self.t0 is not None and self.t1 is not None:
+            # samples taken while the timed region ran (the sampler itself starts before warm-up so
+            # that short regions still get samples); fall back to the nearest ones if none landed
+            inside = [x for x in lines if self.t0 <= x[0] <= self.t1 + 0.06]
+            lines = inside or sorted(lines, key=lambda x: abs(x[0] - self.t1))[:2]
+        for _, ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -175,6 +188,16 @@ def barrier(dist):
         dist.barrier()
 
 
+def all_ranks(dist, x):
+    if dist is None:
+        return [x]
+    import torch
+
+    out = [torch.zeros(1, dtype=torch.float64) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, torch.tensor([x], dtype=torch.float64))
+    return [round(float(t.item()), 3) for t in out]
+
+
 def max_over_ranks(dist, x):
     if dist is None:
         return x
@@ -202,17 +225,18 @@ def bench_mlp(dev, dist, rank, world, steps, warmup, peaks):
     def step():
         return W.mlp_train_step(X, Y, params, LR, dp)
 
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", 0)))
+    sampler.start()
     loss = None
     for _ in range(warmup):
         loss = step()      # same object lifetimes as the timed loop, so the allocator pool has converged
     dev.sync()
     # ---- timed region: inputs resident in HBM
-    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", 0)))
     e0, e1 = dev.event(), dev.event()
     dev.prof(True)
     barrier(dist)
     dev.sync()
-    sampler.start()
+    sampler.mark_begin()
     l0 = dev.launches()
     allocs0 = dev.mem()["device_allocs"]
     dev.record(e0)
@@ -220,6 +244,7 @@ def bench_mlp(dev, dist, rank, world, steps, warmup, peaks):
         loss = step()
     dev.record(e1)
     dev.sync()
+    sampler.mark_end()
     barrier(dist)
     ms = dev.elapsed_ms(e0, e1)
     launches = dev.launches() - l0
@@ -230,23 +255,25 @@ def bench_mlp(dev, dist, rank, world, steps, warmup, peaks):
     ew_ms, ew_n, ew_bytes = dev.prof_read(0)
     red_ms, red_n, red_bytes = dev.prof_read(1)
     dev.prof(False)
+    rank_ms = all_ranks(dist, ms / steps)
     ms = max_over_ranks(dist, ms)
     loss_value = float(loss.item())
 
-    # ---- e2e: host (pinned) inputs copied every step, loss read back every step
-    Xh, kx = dev.pinned(X_np)
-    Yh, ky = dev.pinned(Y_np)
+    # ---- e2e: host (pinned) inputs copied every step through the public input pipeline
+    # (HostBatchFeeder: the upload of batch i+1 overlaps step i), loss read back every step
+    feeder = W.HostBatchFeeder(X_np, Y_np)
+    last = None
     for _ in range(3):
-        dev.upload_into(X, Xh); dev.upload_into(Y, Yh); last = float(step().item())
+        Xd, Yd = feeder.next()
+        last = float(W.mlp_train_step(Xd, Yd, params, LR, dp).item())
     barrier(dist)
     dev.sync()
     t0 = time.perf_counter()
     f0, f1 = dev.event(), dev.event()
     dev.record(f0)
-    for _ in range(steps):
-        dev.upload_into(X, Xh)
-        dev.upload_into(Y, Yh)
-        last = float(step().item())            # D2H read of the loss (4 bytes) every step
+    for i in range(steps):
+        Xd, Yd = feeder.next(prefetch_following=True)
+        last = float(W.mlp_train_step(Xd, Yd, params, LR, dp).item())   # D2H read of the loss every step
     dev.record(f1)
     dev.sync()
     barrier(dist)
@@ -267,8 +294,9 @@ def bench_mlp(dev, dist, rank, world, steps, warmup, peaks):
                    "l2": "working set per step (inputs+activations+grads >= 1.3 GB per GPU) exceeds "
                          "the 126 MB L2, no flush needed"},
         "loss": loss_value,
+        "ms_per_step_by_rank": rank_ms,
         "e2e": {"value": GLOBAL_BATCH * steps / (e2e_ms * 1e-3), "unit": "samples/s",
-                "h2d_bytes_per_step": int(X_np.nbytes + Y_np.nbytes), "d2h_bytes_per_step": 4,
+                "h2d_bytes_per_step": int(feeder.bytes_per_step), "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms / steps, "wall_ms_per_step": wall_ms / steps},
         "gpu_launches": launches,
         "memory": mem,
@@ -293,7 +321,6 @@ def bench_mlp(dev, dist, rank, world, steps, warmup, peaks):
                        "frac_of_hbm": red_bytes / (red_ms * 1e-3) / 1e9 / peaks["hbm_gbs"] if red_ms else None},
         },
     }
-    del kx, ky
     return out
 
 

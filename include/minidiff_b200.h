@@ -111,6 +111,11 @@ int mdb_host_free(void* ptr);
 int mdb_h2d(void* dst, const void* src, size_t bytes);         /* async if src is pinned          */
 int mdb_d2h(void* dst, const void* src, size_t bytes);         /* waits for completion            */
 int mdb_d2d(void* dst, const void* src, size_t bytes);
+/* input pipeline: upload the NEXT batch from pinned host memory on a copy stream while the current
+ * step computes.  The copy is ordered after all compute work enqueued before the call (the last
+ * reader of dst); mdb_prefetch_wait() orders later compute after the most recent prefetch. */
+int mdb_prefetch_h2d(void* dst, const void* src, size_t bytes);
+int mdb_prefetch_wait(void);
 
 /* timing on the compute stream (bench.py: CUDA events on the launching stream) */
 int mdb_event_create(void** ev);

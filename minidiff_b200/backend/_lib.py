@@ -72,6 +72,8 @@ _SIGS = {
     "mdb_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "mdb_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "mdb_d2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "mdb_prefetch_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "mdb_prefetch_wait": (C.c_int, []),
     "mdb_event_create": (C.c_int, [_P(C.c_void_p)]),
     "mdb_event_record": (C.c_int, [C.c_void_p]),
     "mdb_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_void_p, _P(C.c_float)]),

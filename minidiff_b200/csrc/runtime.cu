@@ -271,6 +271,31 @@ int mdb_d2h(void* dst, const void* src, size_t bytes) {
   MDB_CUDA(cudaStreamSynchronize(g_stream));
   return 0;
 }
+// Input prefetch: H2D on a dedicated copy stream so the next batch uploads while the current step
+// computes.  The copy first waits for the compute work enqueued so far (the previous user of `dst`),
+// mdb_prefetch_wait() then orders the compute stream after the copy.
+static cudaStream_t g_copy_stream = nullptr;
+static cudaEvent_t g_ev_compute_done = nullptr, g_ev_copy_done = nullptr;
+
+int mdb_prefetch_h2d(void* dst, const void* src, size_t bytes) {
+  MDB_TRY(ensure_init());
+  if (!g_copy_stream) {
+    MDB_CUDA(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
+    MDB_CUDA(cudaEventCreateWithFlags(&g_ev_compute_done, cudaEventDisableTiming));
+    MDB_CUDA(cudaEventCreateWithFlags(&g_ev_copy_done, cudaEventDisableTiming));
+  }
+  MDB_CUDA(cudaEventRecord(g_ev_compute_done, g_stream));
+  MDB_CUDA(cudaStreamWaitEvent(g_copy_stream, g_ev_compute_done, 0));
+  if (bytes) MDB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_copy_stream));
+  MDB_CUDA(cudaEventRecord(g_ev_copy_done, g_copy_stream));
+  return 0;
+}
+
+int mdb_prefetch_wait(void) {
+  if (g_copy_stream) MDB_CUDA(cudaStreamWaitEvent(g_stream, g_ev_copy_done, 0));
+  return 0;
+}
+
 int mdb_d2d(void* dst, const void* src, size_t bytes) {
   MDB_TRY(ensure_init());
   if (bytes) MDB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, g_stream));

@@ -55,7 +55,16 @@ class DataParallel:
             check(lib.mdb_comm_unique_id(uid, path))
         box = [bytes(uid.raw)]
         dist.broadcast_object_list(box, src=0)
-        check(lib.mdb_comm_init(self.rank, self.world, box[0], path))
+        # NCCL prints its version banner on stdout; keep stdout clean for callers that parse it
+        import sys
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            check(lib.mdb_comm_init(self.rank, self.world, box[0], path))
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
         if overlap:
             for p in self.params:
                 p._grad_hook = self._on_grad_ready

@@ -107,3 +107,46 @@ def hvp(X, Y, params, vs):
         s = t if s is None else s + t
     s.backward()
     return [p.grad for p in params]
+
+
+class HostBatchFeeder:
+    """Double-buffered input pipeline for training from host memory: while step i computes on device
+    buffers i % 2, batch i + 1 is uploaded from pinned host memory on the library's copy stream
+    (mdb_prefetch_h2d).  `next()` returns the (X, Y) Tensors for the step that is about to run."""
+
+    def __init__(self, X_np, Y_np):
+        import ctypes as C
+
+        from minidiff_b200.backend._lib import check, lib
+
+        self._C, self._check, self._lib = C, check, lib
+        self._host = [self._pin(X_np), self._pin(Y_np)]
+        self._dev = [(md.Tensor(md.backend.zeros(X_np.shape, dtype=np.float32)),
+                      md.Tensor(md.backend.zeros(Y_np.shape, dtype=np.float32))) for _ in range(2)]
+        self._i = 0
+        self._issued = False
+        self.bytes_per_step = X_np.nbytes + Y_np.nbytes
+
+    def _pin(self, arr):
+        C = self._C
+        p = C.c_void_p()
+        self._check(self._lib.mdb_host_alloc(arr.nbytes, C.byref(p)))
+        view = np.frombuffer((C.c_char * arr.nbytes).from_address(p.value), dtype=arr.dtype).reshape(arr.shape)
+        view[...] = arr
+        return view, p
+
+    def _upload(self, slot):
+        for t, (view, _) in zip(self._dev[slot], self._host):
+            self._check(self._lib.mdb_prefetch_h2d(t._data.ptr, view.ctypes.data, view.nbytes))
+
+    def next(self, prefetch_following=True):
+        slot = self._i % 2
+        if not self._issued:                       # very first batch: nothing was prefetched yet
+            self._upload(slot)
+        self._check(self._lib.mdb_prefetch_wait())  # compute waits for this batch's copy
+        self._issued = False
+        if prefetch_following:                     # start the next batch's upload behind this step
+            self._upload(1 - slot)
+            self._issued = True
+        self._i += 1
+        return self._dev[slot]

@@ -443,3 +443,23 @@ def test_custom_op_via_create_op_func(md):
     y.backward()
     np.testing.assert_allclose(y.as_numpy(), x_np / (np.abs(x_np) + 1), rtol=1e-6)
     np.testing.assert_allclose(x.grad.as_numpy(), 1 / (np.abs(x_np) + 1) ** 2, rtol=1e-6)
+
+
+def test_host_batch_feeder_pipeline_matches_resident_inputs(md):
+    """e2e input pipeline (pinned host -> copy stream -> double-buffered device inputs) must feed
+    exactly the bytes given, step after step, while uploads overlap compute."""
+    from minidiff_b200 import workloads as W
+
+    dims, B = (64, 128, 128, 32), 512
+    X, Y = orc.mlp_data(B, dims[0], dims[-1])
+    ref = [md.Tensor(p.copy(), allow_grad=True) for p in orc.mlp_params(dims)]
+    got = [md.Tensor(p.copy(), allow_grad=True) for p in orc.mlp_params(dims)]
+    feeder = W.HostBatchFeeder(X, Y)
+    Xr, Yr = md.Tensor(X), md.Tensor(Y)
+    for _ in range(4):
+        l_ref = W.mlp_train_step(Xr, Yr, ref, 0.05)
+        Xd, Yd = feeder.next()
+        l_got = W.mlp_train_step(Xd, Yd, got, 0.05)
+        assert float(l_ref.item()) == float(l_got.item())
+    for a, b in zip(ref, got):
+        np.testing.assert_array_equal(a.as_numpy(), b.as_numpy())
