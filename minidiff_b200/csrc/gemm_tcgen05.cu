@@ -394,6 +394,308 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   }
 }
 
+
+// =====================================================================================================
+// CTA-PAIR kernel (cta_group::2): one 256 x 256 output tile per pair of SMs, RAW mode only.
+//
+// Why: at M=128, N=128 a kind::tf32 MMA reads 8 KB of shared memory per 64 tensor-core cycles -- the
+// whole 128 B/clk of an SM -- and the TMA writes (32 KB per k-block) and the converter warps (64 KB per
+// k-block) compete for the same port: ncu showed the single-CTA kernel at 47-54 % tensor-pipe
+// utilisation with the LSU shared-memory share at 43 % (profiles/r01_gemm_raw_ncu.md).  As a pair,
+// each SM still stages a 128-row A tile and a 128-row B tile per k-block (same 32 KB raw + 32 KB lo),
+// but every MMA is 256 x 256 x 8: each SM's tensor core works 128 cycles on the same 8 KB, so the
+// operand traffic per flop halves (MMA 64 B/clk + converters 42 + TMA 21 = ~125 B/clk).
+//
+//   CTA r of the pair loads   A rows  [m0 + 128 r, +128)   and   B rows (n) [n0 + 128 r, +128)
+//   and owns accumulator rows [m0 + 128 r, +128) x all 256 columns in ITS tensor memory.
+//
+// Protocol (barriers live at the same offsets in both CTAs):
+//   hi_full   local   TMA complete_tx                       -> local converters
+//   lo_full   LEADER  one arrive per converter warp of BOTH CTAs (release.cluster) -> leader MMA warp;
+//                     it also covers "raw tiles landed" for both CTAs (converters waited on hi_full)
+//   hi_empty / lo_empty / tmem_full   both   multicast tcgen05.commit from the leader
+//   tmem_empty LEADER one arrive per epilogue warp of both CTAs
+// 512 threads: control warpgroup (TMA, MMA, TMEM alloc), 2 epilogue warpgroups (128 columns each,
+// 128 fp32 promotion registers per thread), 1 converter warpgroup; setmaxnreg 40 / 200 / 64 from a
+// launch value of 128.  setmaxnreg.inc only draws on registers that other warps RELEASED with .dec
+// (a first version launched 640 threads at 96 and asked for more than was released: it hung in .inc),
+// so the shares balance: released 88*128 + 64*128 = 19456 >= requested 72*256 = 18432.
+constexpr int kPairThreads = 512;
+constexpr int kPairConvWarps = 4, kPairEpiWarps = 8;
+constexpr int PBN = 128;          // B rows staged per CTA; the UMMA N is 2 * PBN
+
+struct PairParams {
+  int M, N, K;
+  int a_mn_major, b_mn_major;
+  float* C;
+  int64_t ldc;
+  int accumulate;
+  int tiles_m, tiles_n, group_m;   // in 256 x 256 pair tiles
+  int flags;
+};
+
+template <int kHi, int kLo>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
+gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                        const PairParams p) {
+  using S = Smem<PBN, kHi, kLo>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* lo_ring = smem + S::HI_BYTES;
+  uint64_t* hi_full = (uint64_t*)(smem + S::HI_BYTES + S::LO_BYTES);
+  uint64_t* hi_empty = hi_full + kHi;
+  uint64_t* lo_full = hi_empty + kHi;
+  uint64_t* lo_empty = lo_full + kLo;
+  uint64_t* tmem_full = lo_empty + kLo;          // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int first_tile = (int)cluster_id_x(), tile_step = (int)num_clusters_x();
+  constexpr uint32_t kTmemCols = 512;            // two 256-column accumulator stages
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int num_k = (p.K + BK - 1) / BK;
+  Params tp;                                     // tile_coords() only reads these three
+  tp.tiles_m = p.tiles_m; tp.tiles_n = p.tiles_n; tp.group_m = p.group_m;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kHi; ++s) { mbar_init(&hi_full[s], 1); mbar_init(&hi_empty[s], 1); }
+    for (int s = 0; s < kLo; ++s) { mbar_init(&lo_full[s], 2 * kPairConvWarps); mbar_init(&lo_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 2 * kPairEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  __syncwarp();
+  tcgen05_fence_before();
+  cluster_sync_all();                            // both CTAs' barriers are initialised, TMEM allocated
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 2 || warp == 3) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  } else if (warp == 0) {
+    // ===================================== TMA producer (both CTAs) ==========================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (lane == 0) {
+      Ring hi;
+      for (int t = first_tile; t < num_tiles; t += tile_step) {
+        int m_blk, n_blk;
+        tile_coords(tp, t, m_blk, n_blk);
+        const int m0 = m_blk * 256 + (int)rank * BM, n0 = n_blk * 256 + (int)rank * PBN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          const int k0 = (p.flags & 4096) ? (kb & 7) * BK : kb * BK;   // 4096: timing experiment, L2-resident k range
+          mbar_wait(&hi_empty[hi.slot], hi.phase ^ 1);
+          const uint32_t a_hi = smem_u32(smem + hi.slot * S::SLOT_BYTES), b_hi = a_hi + S::A_BYTES;
+          uint64_t* hbar = &hi_full[hi.slot];
+          mbar_expect_tx(hbar, S::SLOT_BYTES);
+          if (!p.a_mn_major) {
+            tma_load_2d(a_hi, &map_a, hbar, k0, m0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 32; ++c) tma_load_2d(a_hi + c * 4096, &map_a, hbar, m0 + 32 * c, k0);
+          }
+          if (!p.b_mn_major) {
+            tma_load_2d(b_hi, &map_b, hbar, k0, n0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < PBN / 32; ++c) tma_load_2d(b_hi + c * 4096, &map_b, hbar, n0 + 32 * c, k0);
+          }
+          hi.advance(kHi);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer (leader CTA only) ======================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (rank == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn_major << 15) |
+                             ((uint32_t)p.b_mn_major << 16) | ((uint32_t)((2 * PBN) >> 3) << 17) |
+                             ((uint32_t)(256 >> 4) << 24);
+      const uint32_t a_lbo = p.a_mn_major ? 4096 : 16, b_lbo = p.b_mn_major ? 4096 : 16;
+      const uint32_t a_sbo = p.a_mn_major ? 512 : 1024, b_sbo = p.b_mn_major ? 512 : 1024;
+      const uint32_t a_lt = p.a_mn_major ? 1 : 2, b_lt = p.b_mn_major ? 1 : 2;
+      const uint32_t a_kstep = p.a_mn_major ? 1024 : UMMA_K * 4, b_kstep = p.b_mn_major ? 1024 : UMMA_K * 4;
+      Ring hi, lo;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = first_tile; t < num_tiles; t += tile_step) {
+        for (int kb = 0; kb < num_k; ++kb) {
+          const bool chunk_start = (kb % kChunk) == 0;
+          const bool chunk_end = ((kb + 1) % kChunk) == 0 || kb == num_k - 1;
+          if (chunk_start) {
+            mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1);   // both CTAs drained this accumulator
+            tcgen05_fence_after();
+          }
+          const uint32_t tmem_d = tmem_base + acc * 256;
+          if (p.flags & 32768) mbar_wait(&lo_full[lo.slot], lo.phase);
+          else mbar_wait_cluster(&lo_full[lo.slot], lo.phase);    // raw + lo tiles ready in both CTAs
+          tcgen05_fence_after();
+          if (lane == 0) {
+            const uint32_t a_hi = smem_u32(smem + hi.slot * S::SLOT_BYTES), b_hi = a_hi + S::A_BYTES;
+            const uint32_t a_lo = smem_u32(lo_ring + lo.slot * S::SLOT_BYTES), b_lo = a_lo + S::A_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t da_hi = make_desc(a_hi + k * a_kstep, a_lbo, a_sbo, a_lt);
+              const uint64_t da_lo = make_desc(a_lo + k * a_kstep, a_lbo, a_sbo, a_lt);
+              const uint64_t db_hi = make_desc(b_hi + k * b_kstep, b_lbo, b_sbo, b_lt);
+              const uint64_t db_lo = make_desc(b_lo + k * b_kstep, b_lbo, b_sbo, b_lt);
+              if (p.flags & (128 | 256)) {
+                // timing experiments only (results are wrong): 128 = alternate the two TMEM buffers
+                // between consecutive MMAs (no back-to-back dependency on one accumulator),
+                // 256 = issue only hi*hi (one MMA per k-step)
+                const uint32_t alt = (p.flags & 128) ? tmem_base + (acc ^ 1) * 256 : tmem_d;
+                if (!(p.flags & 256)) {
+                  umma_tf32_pair(tmem_d, da_lo, db_hi, idesc, 1);
+                  umma_tf32_pair(alt, da_hi, db_lo, idesc, 1);
+                }
+                umma_tf32_pair((k & 1) ? alt : tmem_d, da_hi, db_hi, idesc, 1);
+                continue;
+              }
+              umma_tf32_pair(tmem_d, da_lo, db_hi, idesc, !(chunk_start && k == 0));
+              umma_tf32_pair(tmem_d, da_hi, db_lo, idesc, 1);
+              umma_tf32_pair(tmem_d, da_hi, db_hi, idesc, 1);
+            }
+            umma_commit_pair(&lo_empty[lo.slot]);
+            umma_commit_pair(&hi_empty[hi.slot]);
+            if (chunk_end) umma_commit_pair(&tmem_full[acc]);
+          }
+          __syncwarp();
+          hi.advance(kHi);
+          lo.advance(kLo);
+          if (chunk_end && ++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4 + kPairEpiWarps) {
+    // ===================================== converters (both CTAs) ============================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    constexpr int kConv = kPairConvWarps * 32;                     // 128 threads
+    const int t = threadIdx.x - (4 + kPairEpiWarps) * 32;
+    Ring hi, lo;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&hi_full[hi.slot], hi.phase);
+        mbar_wait(&lo_empty[lo.slot], lo.phase ^ 1);
+        const uint32_t src = smem_u32(smem + hi.slot * S::SLOT_BYTES);
+        const uint32_t dst = smem_u32(lo_ring + lo.slot * S::SLOT_BYTES);
+        constexpr int kVecs = S::SLOT_BYTES / 16 / kConv;          // 16 float4 per thread
+        constexpr int kBatch = 8;
+#pragma unroll
+        for (int bt = 0; bt < ((p.flags & 512) ? 0 : kVecs / kBatch); ++bt) {   // 512: timing experiment, no conversion
+          float4 v[kBatch];
+#pragma unroll
+          for (int j = 0; j < kBatch; ++j)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(v[j].x), "=f"(v[j].y), "=f"(v[j].z), "=f"(v[j].w)
+                         : "r"(src + (t + (bt * kBatch + j) * kConv) * 16));
+#pragma unroll
+          for (int j = 0; j < kBatch; ++j) {
+            float e[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float h = __uint_as_float(__float_as_uint(e[i]) & 0xFFFFE000u);   // what the MMA sees
+              if (p.flags & 4) e[i] = __fsub_rn(e[i], h);
+              else e[i] = __uint_as_float((__float_as_uint(__fsub_rn(e[i], h)) + 0x1000u) & 0xFFFFE000u);
+            }
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (t + (bt * kBatch + j) * kConv) * 16),
+                         "f"(e[0]), "f"(e[1]), "f"(e[2]), "f"(e[3])
+                         : "memory");
+          }
+        }
+        if (!(p.flags & 8192)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> visible to UMMA
+        __syncwarp();
+        if (lane == 0) {                                               // tell the leader's MMA warp
+          if (p.flags & 16384) mbar_arrive_cluster_release(&lo_full[lo.slot], 0);   // A/B: 28 % slower
+          else mbar_arrive_cluster(&lo_full[lo.slot], 0);
+        }
+        hi.advance(kHi);
+        lo.advance(kLo);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================== epilogue (both CTAs) ==============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    const int q = warp & 3;                               // TMEM lane quarter this warp may touch
+    const int eh = (warp - 4) >> 2;                       // which 128-column half of the accumulator
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool vec_ok = (p.ldc % 4 == 0) && (((uintptr_t)p.C & 15) == 0);
+    const int num_chunks = (num_k + kChunk - 1) / kChunk;
+    for (int t = first_tile; t < num_tiles; t += tile_step) {
+      int m_blk, n_blk;
+      tile_coords(tp, t, m_blk, n_blk);
+      const int row = m_blk * 256 + (int)rank * BM + q * 32 + lane;
+      const int n0 = n_blk * 256 + eh * 128;
+      float sum[128];
+#pragma unroll
+      for (int j = 0; j < 128; ++j) sum[j] = 0.f;
+      for (int ch = 0; ch < num_chunks; ++ch) {
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + eh * 128 + c * 32);
+          MDB_TMEM_LD32(taddr, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[c * 32 + j] = __fadd_rn(sum[c * 32 + j], __uint_as_float(r[j]));
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (row < p.M) {
+        float* crow = p.C + (int64_t)row * p.ldc;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int col0 = n0 + c * 32;
+          if (vec_ok && col0 + 32 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 v = make_float4(sum[c * 32 + j], sum[c * 32 + j + 1], sum[c * 32 + j + 2], sum[c * 32 + j + 3]);
+              float4* dst = (float4*)(crow + col0 + j);
+              if (p.accumulate) {
+                const float4 o = *dst;
+                v = make_float4(__fadd_rn(o.x, v.x), __fadd_rn(o.y, v.y), __fadd_rn(o.z, v.z), __fadd_rn(o.w, v.w));
+              }
+              *dst = v;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) {
+                float v = sum[c * 32 + j];
+                if (p.accumulate) v = __fadd_rn(crow[col0 + j], v);
+                crow[col0 + j] = v;
+              }
+          }
+        }
+      }
+    }
+  }
+
+  // ------------------------------------------ teardown ---------------------------------------
+  __syncwarp();
+  tcgen05_fence_before();
+  cluster_sync_all();        // no CTA leaves (or frees TMEM) while its peer may still signal / read it
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
 // ---- operand pre-pass: hi = rn_tf32(x), lo = rn_tf32(x - hi) into compact planes ----------------
 // The plane keeps the operand's memory order: [outer][inner] with `inner` the unit-stride axis.
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ src, int64_t s_outer,
@@ -427,6 +729,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
 int g_gemm_flags = 4;   // default: lo is left unrounded (the tensor core truncates it); see mdb_gemm_tune
+                        // bit4 (16): never use the CTA-pair kernel; bit5 (32): always use it when legal
+double g_pair_speedup = 1.45;   // per-flop rate of the pair kernel relative to the single-CTA one
 
 static int load_encode() {
   if (g_encode) return 0;
@@ -498,6 +802,42 @@ static int launch(const CUtensorMap maps[4], const tc::Params& p) {
   return 0;
 }
 
+template <int kHi, int kLo>
+static int launch_pair(const CUtensorMap& map_a, const CUtensorMap& map_b, const tc::PairParams& p) {
+  using S = tc::Smem<tc::PBN, kHi, kLo>;
+  static_assert(S::TOTAL <= 227 * 1024, "shared memory budget");
+  auto kern = tc::gemm_3xtf32_pair_kernel<kHi, kLo>;
+  static int max_clusters = 0;
+  if (!max_clusters) {
+    MDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(g_sm_count, 1, 1);
+    cfg.blockDim = dim3(tc::kPairThreads, 1, 1);
+    cfg.dynamicSmemBytes = S::TOTAL;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = g_sm_count / 2;
+    }
+    max_clusters = std::min(n, g_sm_count / 2);
+  }
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int clusters = std::min(tiles, max_clusters);
+  kern<<<2 * clusters, tc::kPairThreads, S::TOTAL, g_stream>>>(map_a, map_b, p);
+  MDB_CHECK_LAUNCH();
+  return 0;
+}
+
+// Wave efficiency of a persistent grid: useful tile-slots / occupied tile-slots.
+static double wave_eff(int64_t tiles, int workers) {
+  const int64_t waves = (tiles + workers - 1) / workers;
+  return (double)tiles / (double)(waves * workers);
+}
+
 // Can TMA read this operand in place?  Needs a unit stride along k (K-major) or along m/n
 // (MN-major), a 16-byte aligned base and a row pitch that is a multiple of 16 bytes.
 static bool tma_addressable(const float* ptr, int64_t s_mn, int64_t s_k, int mn, int k, bool* mn_major,
@@ -546,6 +886,29 @@ int gemm_tcgen05(const mdb_array* c, const mdb_array* a, const mdb_array* b, int
     MDB_TRY(make_map(&maps[2], (const float*)pb.hi.ptr, pb.inner, pb.outer, pb.ld, b_box, pb.mn_major));
     MDB_TRY(make_map(&maps[3], (const float*)pb.lo.ptr, pb.inner, pb.outer, pb.ld, b_box, pb.mn_major));
     p.a_mn_major = pa.mn_major; p.b_mn_major = pb.mn_major;
+  }
+  if (raw && !(g_gemm_flags & 16) && M > tc::BM && N > tc::PBN) {
+    // CTA-pair kernel unless wave quantisation of its 256 x 256 tiles eats the gain (measured ratio
+    // of the two kernels' per-flop rates: see profiles/)
+    const int64_t pm = (M + 255) / 256, pn = (N + 255) / 256;
+    const int64_t sm = (M + tc::BM - 1) / tc::BM, sn = (N + BN - 1) / BN;
+    const double useful_pair = (double)M * N / ((double)pm * pn * 65536.0);
+    const double useful_single = (double)M * N / ((double)sm * sn * 16384.0);
+    const double e_pair = wave_eff(pm * pn, g_sm_count / 2) * useful_pair * g_pair_speedup;
+    const double e_single = wave_eff(sm * sn, g_sm_count) * useful_single;
+    if (e_pair >= e_single || (g_gemm_flags & 32)) {
+      tc::PairParams q;
+      q.M = (int)M; q.N = (int)N; q.K = (int)K;
+      q.a_mn_major = a_mn; q.b_mn_major = b_mn;
+      q.C = (float*)c->ptr; q.ldc = c->strides[0];
+      q.accumulate = accumulate;
+      q.tiles_m = (int)pm; q.tiles_n = (int)pn; q.group_m = 8;
+      q.flags = g_gemm_flags;
+      if (g_gemm_flags & 64) return launch_pair<5, 2>(maps[0], maps[2], q);   // A/B switches
+      if (g_gemm_flags & 1024) return launch_pair<6, 1>(maps[0], maps[2], q);
+      if (g_gemm_flags & 2048) return launch_pair<2, 3>(maps[0], maps[2], q);
+      return launch_pair<4, 3>(maps[0], maps[2], q);
+    }
   }
   p.raw = raw ? 1 : 0;
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
