@@ -42,7 +42,9 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "tc_common.cuh"
 
@@ -411,15 +413,27 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 //
 // Protocol (barriers live at the same offsets in both CTAs):
 //   hi_full   local   TMA complete_tx                       -> local converters
-//   lo_full   LEADER  one arrive per converter warp of BOTH CTAs (release.cluster) -> leader MMA warp;
+//   lo_full   LEADER  one arrive per converter warp of BOTH CTAs -> leader MMA warp;
 //                     it also covers "raw tiles landed" for both CTAs (converters waited on hi_full)
 //   hi_empty / lo_empty / tmem_full   both   multicast tcgen05.commit from the leader
 //   tmem_empty LEADER one arrive per epilogue warp of both CTAs
+// Remote arrives use the plain mbarrier.arrive.shared::cluster form (tc_common.cuh explains why the
+// .release.cluster form is ~1000 cycles slower and what makes the plain one sufficient here).
 // 512 threads: control warpgroup (TMA, MMA, TMEM alloc), 2 epilogue warpgroups (128 columns each,
 // 128 fp32 promotion registers per thread), 1 converter warpgroup; setmaxnreg 40 / 200 / 64 from a
 // launch value of 128.  setmaxnreg.inc only draws on registers that other warps RELEASED with .dec
 // (a first version launched 640 threads at 96 and asked for more than was released: it hung in .inc),
 // so the shares balance: released 88*128 + 64*128 = 19456 >= requested 72*256 = 18432.
+//
+// Where the time goes (MDB_GEMM_TIMING=1 build, 8192^3, cycles per k-block; the MMAs of one k-block
+// need 12 x 128 = 1536 tensor-core cycles):   period 1805 = 85 % tensor-pipe utilisation
+//   converter: work 1216 + fence/arrive 253 + waits 185      MMA warp: waits for lo_full 612
+//   TMA producer: waits for hi_empty 1135 (never the bottleneck)
+// The converter is throughput-bound on the shared-memory port, which the three clients share:
+// tensor core 768 wavefronts of 128 B per k-block, converter 256 (LDS) + 256 (STS), TMA writes 256
+// = 1536 wavefronts per k-block at 1 wavefront/clk -- the same 1536 cycles the MMAs need.  The
+// kernel sits at that shared-memory roofline; software-pipelining the converter loads, deeper
+// rings (<5,2>, <6,1>) and dropping two thirds of the MMAs all leave the period unchanged.
 constexpr int kPairThreads = 512;
 constexpr int kPairConvWarps = 4, kPairEpiWarps = 8;
 constexpr int PBN = 128;          // B rows staged per CTA; the UMMA N is 2 * PBN
@@ -432,9 +446,13 @@ struct PairParams {
   int accumulate;
   int tiles_m, tiles_n, group_m;   // in 256 x 256 pair tiles
   int flags;
+  unsigned long long* timing;      // MDB_GEMM_TIMING=1: per-CTA stall-cycle counters (16 per CTA), else null
 };
 
-template <int kHi, int kLo>
+#define MDB_T0() (kTiming ? clock64() : 0ll)
+#define MDB_TACC(var, t0) do { if (kTiming) var += clock64() - (t0); } while (0)
+
+template <int kHi, int kLo, bool kTiming>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                         const PairParams p) {
@@ -488,13 +506,16 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (lane == 0) {
       Ring hi;
+      long long w_empty = 0, t_all = MDB_T0();
       for (int t = first_tile; t < num_tiles; t += tile_step) {
         int m_blk, n_blk;
         tile_coords(tp, t, m_blk, n_blk);
         const int m0 = m_blk * 256 + (int)rank * BM, n0 = n_blk * 256 + (int)rank * PBN;
         for (int kb = 0; kb < num_k; ++kb) {
-          const int k0 = (p.flags & 4096) ? (kb & 7) * BK : kb * BK;   // 4096: timing experiment, L2-resident k range
+          const int k0 = (kTiming && (p.flags & 4096)) ? (kb & 7) * BK : kb * BK;   // 4096: diagnostic, L2-resident k range
+          const long long tw = MDB_T0();
           mbar_wait(&hi_empty[hi.slot], hi.phase ^ 1);
+          MDB_TACC(w_empty, tw);
           const uint32_t a_hi = smem_u32(smem + hi.slot * S::SLOT_BYTES), b_hi = a_hi + S::A_BYTES;
           uint64_t* hbar = &hi_full[hi.slot];
           mbar_expect_tx(hbar, S::SLOT_BYTES);
@@ -513,6 +534,7 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
           hi.advance(kHi);
         }
       }
+      if (kTiming) { p.timing[blockIdx.x * 16 + 0] = w_empty; p.timing[blockIdx.x * 16 + 1] = clock64() - t_all; }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer (leader CTA only) ======================
@@ -528,17 +550,21 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
       Ring hi, lo;
       int acc = 0;
       uint32_t acc_phase = 0;
+      long long w_lo = 0, w_tmem = 0, t_all = MDB_T0();
       for (int t = first_tile; t < num_tiles; t += tile_step) {
         for (int kb = 0; kb < num_k; ++kb) {
           const bool chunk_start = (kb % kChunk) == 0;
           const bool chunk_end = ((kb + 1) % kChunk) == 0 || kb == num_k - 1;
           if (chunk_start) {
+            const long long tw = MDB_T0();
             mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1);   // both CTAs drained this accumulator
+            MDB_TACC(w_tmem, tw);
             tcgen05_fence_after();
           }
           const uint32_t tmem_d = tmem_base + acc * 256;
-          if (p.flags & 32768) mbar_wait(&lo_full[lo.slot], lo.phase);
-          else mbar_wait_cluster(&lo_full[lo.slot], lo.phase);    // raw + lo tiles ready in both CTAs
+          const long long tw2 = MDB_T0();
+          mbar_wait_cluster(&lo_full[lo.slot], lo.phase);    // raw + lo tiles ready in both CTAs
+          MDB_TACC(w_lo, tw2);
           tcgen05_fence_after();
           if (lane == 0) {
             const uint32_t a_hi = smem_u32(smem + hi.slot * S::SLOT_BYTES), b_hi = a_hi + S::A_BYTES;
@@ -549,8 +575,8 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
               const uint64_t da_lo = make_desc(a_lo + k * a_kstep, a_lbo, a_sbo, a_lt);
               const uint64_t db_hi = make_desc(b_hi + k * b_kstep, b_lbo, b_sbo, b_lt);
               const uint64_t db_lo = make_desc(b_lo + k * b_kstep, b_lbo, b_sbo, b_lt);
-              if (p.flags & (128 | 256)) {
-                // timing experiments only (results are wrong): 128 = alternate the two TMEM buffers
+              if (kTiming && (p.flags & (128 | 256))) {
+                // diagnostic build only (results are wrong): 128 = alternate the two TMEM buffers
                 // between consecutive MMAs (no back-to-back dependency on one accumulator),
                 // 256 = issue only hi*hi (one MMA per k-step)
                 const uint32_t alt = (p.flags & 128) ? tmem_base + (acc ^ 1) * 256 : tmem_d;
@@ -575,6 +601,10 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
           if (chunk_end && ++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
       }
+      if (kTiming && lane == 0) {
+        p.timing[blockIdx.x * 16 + 2] = w_lo; p.timing[blockIdx.x * 16 + 3] = w_tmem;
+        p.timing[blockIdx.x * 16 + 4] = clock64() - t_all;
+      }
     }
   } else if (warp >= 4 + kPairEpiWarps) {
     // ===================================== converters (both CTAs) ============================
@@ -582,45 +612,67 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     constexpr int kConv = kPairConvWarps * 32;                     // 128 threads
     const int t = threadIdx.x - (4 + kPairEpiWarps) * 32;
     Ring hi, lo;
+    long long w_hi = 0, w_lo = 0, t_work = 0, t_sig = 0, t_all = MDB_T0();
     for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
       for (int kb = 0; kb < num_k; ++kb) {
+        const long long ta = MDB_T0();
         mbar_wait(&hi_full[hi.slot], hi.phase);
+        MDB_TACC(w_hi, ta);
+        const long long tb = MDB_T0();
         mbar_wait(&lo_empty[lo.slot], lo.phase ^ 1);
+        MDB_TACC(w_lo, tb);
+        const long long tc0 = MDB_T0();
         const uint32_t src = smem_u32(smem + hi.slot * S::SLOT_BYTES);
         const uint32_t dst = smem_u32(lo_ring + lo.slot * S::SLOT_BYTES);
         constexpr int kVecs = S::SLOT_BYTES / 16 / kConv;          // 16 float4 per thread
-        constexpr int kBatch = 8;
-#pragma unroll
-        for (int bt = 0; bt < ((p.flags & 512) ? 0 : kVecs / kBatch); ++bt) {   // 512: timing experiment, no conversion
-          float4 v[kBatch];
+        constexpr int kBatch = 4, kBatches = kVecs / kBatch;
+        // software pipeline: the loads of batch b+1 are in flight while batch b is converted and stored
+        // (the LDS latency under tensor-core shared-memory traffic is several hundred cycles)
+        float4 v[2][kBatch];
+        auto load_batch = [&](int bt, float4 (&dstv)[kBatch]) {
 #pragma unroll
           for (int j = 0; j < kBatch; ++j)
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(v[j].x), "=f"(v[j].y), "=f"(v[j].z), "=f"(v[j].w)
+                         : "=f"(dstv[j].x), "=f"(dstv[j].y), "=f"(dstv[j].z), "=f"(dstv[j].w)
                          : "r"(src + (t + (bt * kBatch + j) * kConv) * 16));
+        };
+        if (!(kTiming && (p.flags & 512))) {                       // 512: diagnostic, no conversion
+          load_batch(0, v[0]);
 #pragma unroll
-          for (int j = 0; j < kBatch; ++j) {
-            float e[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+          for (int bt = 0; bt < kBatches; ++bt) {
+            if (bt + 1 < kBatches) load_batch(bt + 1, v[(bt + 1) & 1]);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float h = __uint_as_float(__float_as_uint(e[i]) & 0xFFFFE000u);   // what the MMA sees
-              if (p.flags & 4) e[i] = __fsub_rn(e[i], h);
-              else e[i] = __uint_as_float((__float_as_uint(__fsub_rn(e[i], h)) + 0x1000u) & 0xFFFFE000u);
+            for (int j = 0; j < kBatch; ++j) {
+              const float4 x = v[bt & 1][j];
+              float e[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float h = __uint_as_float(__float_as_uint(e[i]) & 0xFFFFE000u);   // what the MMA sees
+                if (p.flags & 4) e[i] = __fsub_rn(e[i], h);
+                else e[i] = __uint_as_float((__float_as_uint(__fsub_rn(e[i], h)) + 0x1000u) & 0xFFFFE000u);
+              }
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (t + (bt * kBatch + j) * kConv) * 16),
+                           "f"(e[0]), "f"(e[1]), "f"(e[2]), "f"(e[3])
+                           : "memory");
             }
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (t + (bt * kBatch + j) * kConv) * 16),
-                         "f"(e[0]), "f"(e[1]), "f"(e[2]), "f"(e[3])
-                         : "memory");
           }
         }
-        if (!(p.flags & 8192)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> visible to UMMA
+        MDB_TACC(t_work, tc0);
+        const long long td = MDB_T0();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> visible to UMMA
         __syncwarp();
         if (lane == 0) {                                               // tell the leader's MMA warp
-          if (p.flags & 16384) mbar_arrive_cluster_release(&lo_full[lo.slot], 0);   // A/B: 28 % slower
+          if (kTiming && (p.flags & 16384)) mbar_arrive_cluster_release(&lo_full[lo.slot], 0);   // diagnostic: 28 % slower
           else mbar_arrive_cluster(&lo_full[lo.slot], 0);
         }
+        MDB_TACC(t_sig, td);
         hi.advance(kHi);
         lo.advance(kLo);
       }
+    }
+    if (kTiming && t == 0) {
+      unsigned long long* d = p.timing + blockIdx.x * 16;
+      d[6] = w_hi; d[7] = w_lo; d[8] = t_work; d[9] = t_sig; d[10] = clock64() - t_all;
     }
   } else if (warp >= 4) {
     // ===================================== epilogue (both CTAs) ==============================
@@ -631,6 +683,7 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     uint32_t acc_phase = 0;
     const bool vec_ok = (p.ldc % 4 == 0) && (((uintptr_t)p.C & 15) == 0);
     const int num_chunks = (num_k + kChunk - 1) / kChunk;
+    long long w_full = 0, t_all = MDB_T0();
     for (int t = first_tile; t < num_tiles; t += tile_step) {
       int m_blk, n_blk;
       tile_coords(tp, t, m_blk, n_blk);
@@ -640,7 +693,9 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
 #pragma unroll
       for (int j = 0; j < 128; ++j) sum[j] = 0.f;
       for (int ch = 0; ch < num_chunks; ++ch) {
+        const long long tw = MDB_T0();
         mbar_wait(&tmem_full[acc], acc_phase);
+        MDB_TACC(w_full, tw);
         tcgen05_fence_after();
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -683,6 +738,9 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
           }
         }
       }
+    }
+    if (kTiming && warp == 4 && lane == 0) {
+      p.timing[blockIdx.x * 16 + 11] = w_full; p.timing[blockIdx.x * 16 + 12] = clock64() - t_all;
     }
   }
 
@@ -806,7 +864,7 @@ template <int kHi, int kLo>
 static int launch_pair(const CUtensorMap& map_a, const CUtensorMap& map_b, const tc::PairParams& p) {
   using S = tc::Smem<tc::PBN, kHi, kLo>;
   static_assert(S::TOTAL <= 227 * 1024, "shared memory budget");
-  auto kern = tc::gemm_3xtf32_pair_kernel<kHi, kLo>;
+  auto kern = tc::gemm_3xtf32_pair_kernel<kHi, kLo, false>;
   static int max_clusters = 0;
   if (!max_clusters) {
     MDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
@@ -827,8 +885,37 @@ static int launch_pair(const CUtensorMap& map_a, const CUtensorMap& map_b, const
   }
   const int tiles = p.tiles_m * p.tiles_n;
   const int clusters = std::min(tiles, max_clusters);
-  kern<<<2 * clusters, tc::kPairThreads, S::TOTAL, g_stream>>>(map_a, map_b, p);
+  static const bool timing = getenv("MDB_GEMM_TIMING") != nullptr;
+  if (!timing) {
+    kern<<<2 * clusters, tc::kPairThreads, S::TOTAL, g_stream>>>(map_a, map_b, p);
+    MDB_CHECK_LAUNCH();
+    return 0;
+  }
+  // diagnostic mode: per-role stall cycles, averaged over leader / follower CTAs, printed to stderr
+  static unsigned long long* dbuf = nullptr;
+  if (!dbuf) MDB_CUDA(cudaMalloc(&dbuf, 16 * 8 * 2 * 148));
+  MDB_CUDA(cudaMemsetAsync(dbuf, 0, 16 * 8 * 2 * clusters, g_stream));
+  tc::PairParams q = p;
+  q.timing = dbuf;
+  auto tkern = tc::gemm_3xtf32_pair_kernel<kHi, kLo, true>;
+  MDB_CUDA(cudaFuncSetAttribute(tkern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+  tkern<<<2 * clusters, tc::kPairThreads, S::TOTAL, g_stream>>>(map_a, map_b, q);
   MDB_CHECK_LAUNCH();
+  std::vector<unsigned long long> h(16 * 2 * clusters);
+  MDB_CUDA(cudaMemcpyAsync(h.data(), dbuf, h.size() * 8, cudaMemcpyDeviceToHost, g_stream));
+  MDB_CUDA(cudaStreamSynchronize(g_stream));
+  static const char* names[13] = {"prod.wait_hi_empty", "prod.total", "mma.wait_lo_full", "mma.wait_tmem_empty", "mma.total",
+                                  "-", "conv.wait_hi_full", "conv.wait_lo_empty", "conv.work", "conv.fence+arrive",
+                                  "conv.total", "epi.wait_tmem_full", "epi.total"};
+  const double kblocks = (double)((p.K + tc::BK - 1) / tc::BK) * ((tiles + clusters - 1) / clusters);
+  fprintf(stderr, "[gemm timing] M=%d N=%d K=%d kHi=%d kLo=%d flags=%d  (cycles per k-block, leader | follower)\n", p.M, p.N,
+          p.K, kHi, kLo, p.flags);
+  for (int i = 0; i < 13; ++i) {
+    if (i == 5) continue;
+    double s[2] = {0, 0};
+    for (int c = 0; c < 2 * clusters; ++c) s[c & 1] += (double)h[c * 16 + i];
+    fprintf(stderr, "  %-22s %9.1f | %9.1f\n", names[i], s[0] / clusters / kblocks, s[1] / clusters / kblocks);
+  }
   return 0;
 }
 
@@ -904,9 +991,8 @@ int gemm_tcgen05(const mdb_array* c, const mdb_array* a, const mdb_array* b, int
       q.accumulate = accumulate;
       q.tiles_m = (int)pm; q.tiles_n = (int)pn; q.group_m = 8;
       q.flags = g_gemm_flags;
+      q.timing = nullptr;
       if (g_gemm_flags & 64) return launch_pair<5, 2>(maps[0], maps[2], q);   // A/B switches
-      if (g_gemm_flags & 1024) return launch_pair<6, 1>(maps[0], maps[2], q);
-      if (g_gemm_flags & 2048) return launch_pair<2, 3>(maps[0], maps[2], q);
       return launch_pair<4, 3>(maps[0], maps[2], q);
     }
   }

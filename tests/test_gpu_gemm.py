@@ -18,14 +18,18 @@ def B():
     return backend
 
 
-@pytest.fixture()
-def force_tc(B):
-    """tensor-core kernel only (no silent CUDA-core fallback).  RAW mode is taken when TMA can
-    address the operands in place; ragged pitches / doubly strided views take PRE-SPLIT mode."""
+@pytest.fixture(params=["auto", "pair", "single"])
+def force_tc(B, request):
+    """tensor-core kernels only (no silent CUDA-core fallback).  RAW mode is taken when TMA can
+    address the operands in place; ragged pitches / doubly strided views take PRE-SPLIT mode.
+    Every case runs three times: dispatcher's choice, the CTA-pair kernel (cta_group::2, 256x256
+    tiles) wherever it is legal, and the single-CTA kernel (128x128 tiles) only."""
     from minidiff_b200.backend._lib import check, lib
 
     check(lib.mdb_gemm_config(2))
+    check(lib.mdb_gemm_tune({"auto": 4, "pair": 4 | 32, "single": 4 | 16}[request.param]))
     yield
+    check(lib.mdb_gemm_tune(4))
     check(lib.mdb_gemm_config(0))
 
 
@@ -39,7 +43,8 @@ def operands(B, M, K, N, layout, seed=0):
 
 
 SHAPES = [(128, 128, 128), (128, 160, 128), (256, 512, 384), (129, 200, 130), (1000, 777, 555),
-          (384, 4096, 64), (64, 8192, 64), (2048, 1024, 1536)]
+          (384, 4096, 64), (64, 8192, 64), (2048, 1024, 1536), (300, 260, 272), (512, 96, 768),
+          (4352, 512, 2304)]
 
 
 @pytest.mark.parametrize("layout", ["NN", "NT", "TN", "TT"])
