@@ -31,6 +31,20 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# ncu --set full capture of one C4 step at N=1 (profiles/r01_ncu_mlp_step_gemm_pair.md): DRAM bytes per GEMM
+# launch, and the algorithmic figure beside it (each operand read once + C written once, 8 GEMMs/step)
+GEMM_TRAFFIC_BYTES_PER_LAUNCH = 3.802e9
+GEMM_ALGORITHMIC_BYTES_PER_LAUNCH = (
+    # fwd1, fwd2, fwd3 (X@W), dW3, dh2, dW2, dh1, dW1 at B=65536, D=(1024,4096,4096,1024)
+    sum(4.0 * (m * k + k * n + m * n) for m, k, n in [
+        (65536, 1024, 4096), (65536, 4096, 4096), (65536, 4096, 1024),
+        (4096, 65536, 1024), (65536, 1024, 4096), (4096, 65536, 4096), (65536, 4096, 4096),
+        (1024, 65536, 4096)]) / 8.0)
+# C2: DRAM bytes of the 13 launches of one iteration (ncu, profiles/r01_c2_launches_v2.csv)
+C2_TRAFFIC_BYTES_PER_ITER = 3.989e9
+C2_TRAFFIC_SRC = ("dram__bytes_read.sum + dram__bytes_write.sum over the 13 launches of one iteration, "
+                  "profiles/r01_c2_launches_v2.csv (below the algorithmic 4.295e9: part of each output is still "
+                  "in the 126 MB L2 when the next op reads it)")
 GLOBAL_BATCH = 65536
 DIMS = (1024, 4096, 4096, 1024)
 LR = 0.01
@@ -304,13 +318,20 @@ def bench_mlp(dev, dist, rank, world, steps, warmup, peaks):
         "roofline": {
             "bound": "tensor", "kernel": "mdb_gemm (matmul fwd + dW/dX gradient GEMMs)",
             "achieved": gemm_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
-            "frac": gemm_tflops / tf32_peak if tf32_peak else None, "traffic": None,
+            "frac": gemm_tflops / tf32_peak if tf32_peak else None,
+            "pipe_frac": 3.0 * gemm_tflops / tf32_peak if tf32_peak else None,
+            "traffic": GEMM_TRAFFIC_BYTES_PER_LAUNCH if world == 1 else None,
+            "traffic_src": "dram__bytes_read.sum + dram__bytes_write.sum averaged over the 8 GEMM launches of one "
+                           "C4 step, profiles/r01_ncu_mlp_step_gemm_pair.md (same capture: tensor pipe 79-92 % "
+                           "active at the power-capped 1.55-1.68 GHz)",
+            "algorithmic_bytes_per_launch": GEMM_ALGORITHMIC_BYTES_PER_LAUNCH if world == 1 else None,
             "launches": int(gemm_n), "avg_launch_ms": gemm_ms / gemm_n if gemm_n else None,
             "share_of_step": gemm_ms / ms if ms else None,
             "note": "achieved = algorithmic 2MNK flops / CUDA-event time of the GEMM launches inside "
                     "the timed region; peak = TF32 dense peak taken as half the "
                     f"{peaks['src']} sustained bf16 rate ({peaks['bf16_sustained']} TF/s); a 3xTF32 "
-                    "GEMM issues 3 tensor-core MACs per fp32 product, so pipe use = 3*frac",
+                    "GEMM issues 3 tensor-core MACs per fp32 product, so pipe_frac = 3*frac (above 1.0 = more "
+                    "tensor work per second than cuBLAS bf16 sustains under the same power cap)",
         },
         "other_kernels": {
             "elementwise": {"ms_per_step": ew_ms / steps, "calls_per_step": ew_n / steps,
@@ -333,32 +354,44 @@ def bench_c2(dev, steps, warmup, peaks):
     for _ in range(warmup):
         W.c2_step(a, c)
     dev.sync()
+    time.sleep(0.3)          # let the power state settle after the GEMM-heavy headline loop
+    # pass 1: whole-iteration device time, no per-launch profiler events on the stream (the event
+    # pairs cost ~5 us per launch, 8 % of this 13-launch iteration)
     e0, e1 = dev.event(), dev.event()
-    dev.prof(True)
     l0 = dev.launches()
+    t0 = time.perf_counter()
     dev.record(e0)
     for _ in range(steps):
         loss = W.c2_step(a, c)
+    host_ms = (time.perf_counter() - t0) * 1e3 / steps
     dev.record(e1)
     dev.sync()
     ms = dev.elapsed_ms(e0, e1) / steps
     launches = (dev.launches() - l0) / steps
+    # pass 2: per-class split and the algorithmic bytes of OUR launches (profiler on)
+    dev.prof(True)
+    for _ in range(steps):
+        W.c2_step(a, c)
+    dev.sync()
     ew_ms, ew_n, ew_bytes = dev.prof_read(0)
     red_ms, red_n, red_bytes = dev.prof_read(1)
     dev.prof(False)
-    kern_ms, kern_bytes = ew_ms + red_ms, ew_bytes + red_bytes
+    kern_ms, kern_bytes = (ew_ms + red_ms) / steps, (ew_bytes + red_bytes) / steps
     return {
         "workload": "C2 sum(sin(a*c+a)**2).backward(), a:(8192,1) c:(1,8192) fp32 (2^26-element tensors)",
-        "ms_per_iter": ms, "launches_per_iter": launches, "loss": float(loss.item()),
+        "ms_per_iter": ms, "host_issue_ms_per_iter": host_ms, "launches_per_iter": launches,
+        "loss": float(loss.item()),
         "reference_chain_GBps": W.C2_ALGORITHMIC_BYTES / (ms * 1e-3) / 1e9,
         "reference_chain_bytes": W.C2_ALGORITHMIC_BYTES,
         "note": "reference_chain_GBps = the 26E bytes the reference's 22-call chain moves (SURVEY 8d) "
                 "/ our time; fused backward kernels move fewer bytes, so this can exceed the HBM peak. "
-                "The roofline below is per kernel: algorithmic bytes of OUR launches / their event time.",
-        "roofline": {"bound": "hbm", "achieved": kern_bytes / (kern_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
-                     "unit": "GB/s", "frac": kern_bytes / (kern_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                     "traffic": None, "kernel_ms_per_iter": kern_ms / steps,
-                     "algorithmic_bytes_per_iter": kern_bytes / steps,
+                "The roofline below is for OUR launches: their algorithmic bytes / the whole-iteration "
+                "device time (CUDA events around the loop, launch gaps included).",
+        "roofline": {"bound": "hbm", "achieved": kern_bytes / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                     "unit": "GB/s", "frac": kern_bytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                     "traffic": C2_TRAFFIC_BYTES_PER_ITER, "traffic_src": C2_TRAFFIC_SRC,
+                     "algorithmic_bytes_per_iter": kern_bytes,
+                     "kernel_event_ms_per_iter": kern_ms,
                      "inputs": "8 tensors of 256 MiB per iteration > 126 MB L2 (no flush needed)"},
     }
 
@@ -387,8 +420,47 @@ def bench_c3(dev, steps, warmup, peaks, n=8192):
     return {"workload": f"C3 C=A@B; C.backward() {n}^3 fp32 (NN fwd, NT dA, TN dB)",
             "ms_per_iter": ms, "TFLOPs_fp32_equiv": W.c3_flops(n) / (ms * 1e-3) / 1e12,
             "roofline": {"bound": "tensor", "achieved": tf, "peak": tf32_peak, "unit": "TFLOP/s",
-                         "frac": tf / tf32_peak, "traffic": None, "avg_launch_ms": g_ms / g_n,
+                         "frac": tf / tf32_peak, "pipe_frac": 3.0 * tf / tf32_peak,
+                         "traffic": 2.65e9, "traffic_src": "profiles/r01_ncu_c3_gemm_pair_before_arrive_fix.md "
+                         "(DRAM read+write per 8192^3 launch; algorithmic 0.805e9)",
+                         "avg_launch_ms": g_ms / g_n,
                          "note": "peak = half the measured burst bf16 rate; 3xTF32 pipe use = 3*frac"}}
+
+
+def bench_c5(dev, steps, warmup, peaks, batch=8192):
+    """BASELINE config 5: Hessian-vector product through a second-order graph of device ops."""
+    md = dev.md
+    from minidiff_b200 import workloads as W
+
+    X_np, Y_np = W.mlp_data(batch, DIMS[0], DIMS[-1], seed=40)
+    params = [md.Tensor(p, allow_grad=True) for p in W.mlp_params(DIMS)]
+    vs = [md.Tensor(np.random.default_rng(50 + i).standard_normal(p.shape).astype(np.float32))
+          for i, p in enumerate(params)]
+    X, Y = md.Tensor(X_np), md.Tensor(Y_np)
+    for _ in range(warmup):
+        W.hvp(X, Y, params, vs)
+    dev.sync()
+    e0, e1 = dev.event(), dev.event()
+    dev.prof(True)
+    l0 = dev.launches()
+    dev.record(e0)
+    for _ in range(steps):
+        hv = W.hvp(X, Y, params, vs)
+    dev.record(e1)
+    dev.sync()
+    ms = dev.elapsed_ms(e0, e1) / steps
+    g_ms, g_n, g_fl = dev.prof_read(2)
+    dev.prof(False)
+    tf32_peak = peaks["bf16_burst"] / 2.0
+    tf = g_fl / (g_ms * 1e-3) / 1e12
+    return {"workload": f"C5 Hessian-vector product, same MLP, batch {batch}, allow_higher_order backward "
+                        "then backward of sum(grad*v)",
+            "ms_per_iter": ms, "launches_per_iter": (dev.launches() - l0) / steps,
+            "gemm_launches_per_iter": g_n / steps, "gemm_flops_per_iter": g_fl / steps,
+            "hv_norm": float(md.sum(hv[0] * hv[0]).item()) ** 0.5,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": tf32_peak, "unit": "TFLOP/s",
+                         "frac": tf / tf32_peak, "pipe_frac": 3.0 * tf / tf32_peak, "traffic": None,
+                         "gemm_share_of_iter": (g_ms / steps) / ms}}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -414,7 +486,7 @@ def reference_arm(args, rank):
     if rank != 0:
         return
     cores = os.cpu_count()
-    sample = 2048
+    sample = 8192
     times = []
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import np_minidiff as orc
@@ -471,12 +543,13 @@ def main():
     if rank == 0 and world == 1:
         if not args.skip_extras:
             line["fwd_bwd"] = {"c2_broadcast_chain": bench_c2(dev, max(args.steps, 10), warmup, peaks),
-                               "c3_matmul": bench_c3(dev, max(2, min(args.steps, 5)), warmup, peaks)}
+                               "c3_matmul": bench_c3(dev, max(2, min(args.steps, 5)), warmup, peaks),
+                               "c5_hvp": bench_c5(dev, max(args.steps, 10), warmup, peaks)}
         if not args.skip_cpu:
-            v, secs = cpu_mlp_samples_per_s(1024, 2)
+            v, secs = cpu_mlp_samples_per_s(16384, 3)
             line["cpu_baseline"] = {
                 "value": v, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
-                "sample": f"one full training step on a 1024-row sample of the batch, best of 2 "
+                "sample": f"one full training step on a 16384-row sample of the batch, best of 3 "
                           f"({secs:.2f} s each); NumPy {np.__version__}/OpenBLAS, matmul on all host "
                           "threads, elementwise single-threaded"}
     if rank == 0:

@@ -122,7 +122,7 @@ template <int OP, int NIN, int VEC, bool FLAT, bool CHECK>
 __device__ __forceinline__ void ew_fast_body(const FastParams& p, uint32_t base, uint32_t stride) {
   constexpr int U = 4;
   constexpr bool PRED = op_is_predicate(OP);
-  float v[U][3][VEC];
+  uint32_t raw[U][NIN][VEC];
   int64_t ooff[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
@@ -140,17 +140,19 @@ __device__ __forceinline__ void ew_fast_body(const FastParams& p, uint32_t base,
         ooff[u] = (int64_t)(int32_t)i2 * (int64_t)p.os2 + (int64_t)(int32_t)i1 * (int64_t)p.os1 + col;
       }
 #pragma unroll
-      for (int k = 0; k < NIN; ++k) fast_load<VEC>(p.in[k], i2, i1, col, v[u][k]);
+      for (int k = 0; k < NIN; ++k) fast_load_raw<VEC>(p.in[k], i2, i1, col, raw[u][k]);
     }
   }
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     const uint32_t w = base + u * stride;
     if (!CHECK || w < p.total) {
-      float r[VEC];
+      float v[3][VEC], r[VEC];
+#pragma unroll
+      for (int k = 0; k < NIN; ++k) fast_decode<VEC>(p.in[k], raw[u][k], v[k]);
 #pragma unroll
       for (int j = 0; j < VEC; ++j)
-        r[j] = apply<OP, float>(v[u][0][j], NIN > 1 ? v[u][1][j] : 0.f, NIN > 2 ? v[u][2][j] : 0.f, p.aux);
+        r[j] = apply<OP, float>(v[0][j], NIN > 1 ? v[1][j] : 0.f, NIN > 2 ? v[2][j] : 0.f, p.aux);
       if constexpr (PRED) {
         unsigned char* o = (unsigned char*)p.out + ooff[u];
         if constexpr (VEC == 4) *(uchar4*)o = make_uchar4(r[0] != 0.f, r[1] != 0.f, r[2] != 0.f, r[3] != 0.f);
@@ -165,7 +167,7 @@ __device__ __forceinline__ void ew_fast_body(const FastParams& p, uint32_t base,
 }
 
 template <int OP, int NIN, int VEC, bool FLAT>
-__global__ void __launch_bounds__(256) ew_fast(const FastParams p) {
+__global__ void __launch_bounds__(256, NIN == 1 ? 6 : (NIN == 2 ? 4 : 3)) ew_fast(const FastParams p) {
   constexpr uint32_t U = 4;
   const uint32_t stride = gridDim.x * blockDim.x;
   uint32_t base = blockIdx.x * blockDim.x + threadIdx.x;
@@ -344,7 +346,8 @@ int elementwise_impl(int op, const mdb_array* out, int n_in, const mdb_array* in
       p.total = (uint32_t)items;
       p.div_lv = FastDiv((uint32_t)(L / vec));
       p.div_d1 = FastDiv((uint32_t)d1);
-      int grid = grid_for((items + 3) / 4, 256);
+      const int per_thread = 4;
+      int grid = grid_for((items + per_thread - 1) / per_thread, 256);
       switch (op) {
 #define X(OPID) case OPID: return launch_fast<OPID, 1>(p, vec, flat, grid);
         MDB_UNARY_OPS(X)

@@ -254,40 +254,53 @@ struct FastOperand {
   int kind;
   float imm;
 };
+// Loads are split in two phases so that nothing DEPENDS on a load until every load of the thread is
+// in flight: fast_load_raw only issues the load (raw bits, no broadcast copies, no u8 -> float
+// conversion), fast_decode turns the raw bits into the VEC operand values at compute time.
+// (ncu on the first version: the `v[j] = s` copies of a stride-0 operand and the I2F of a mask sat
+// right behind their load, so the 4 work items of a thread were serialised on L2 latency --
+// long_scoreboard 14-22 cycles per issue, 0.47-0.79 of the HBM roofline on broadcast forms.)
 template <int VEC>
-__device__ __forceinline__ void fast_load(const FastOperand& o, uint32_t i2, uint32_t i1,
-                                          uint32_t col, float (&v)[VEC]) {
-  if (o.kind == K_IMM) {
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) v[j] = o.imm;
-    return;
-  }
+__device__ __forceinline__ void fast_load_raw(const FastOperand& o, uint32_t i2, uint32_t i1,
+                                              uint32_t col, uint32_t (&raw)[VEC]) {
+  if (o.kind == K_IMM) return;
   const int64_t off = (int64_t)(int32_t)i2 * (int64_t)o.s2 + (int64_t)(int32_t)i1 * (int64_t)o.s1;
   if (o.kind == K_F32) {
     const float* p = (const float*)o.ptr + off;
     if (o.s0 == 0) {
-      float s = __ldg(p);
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) v[j] = s;
+      raw[0] = __float_as_uint(__ldg(p));
     } else if constexpr (VEC == 4) {
-      float4 q = __ldg((const float4*)(p + col));
-      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+      const uint4 q = __ldg((const uint4*)(p + col));
+      raw[0] = q.x; raw[1] = q.y; raw[2] = q.z; raw[3] = q.w;
     } else {
-      v[0] = __ldg(p + col);
+      raw[0] = __float_as_uint(__ldg(p + col));
     }
   } else {
     const unsigned char* p = (const unsigned char*)o.ptr + off;
-    if (o.s0 == 0) {
-      float s = (float)__ldg(p);
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) v[j] = s;
-    } else if constexpr (VEC == 4) {
-      uchar4 q = __ldg((const uchar4*)(p + col));
-      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-    } else {
-      v[0] = (float)__ldg(p + col);
-    }
+    if (o.s0 == 0) raw[0] = __ldg(p);
+    else if constexpr (VEC == 4) raw[0] = __ldg((const unsigned int*)(p + col));
+    else raw[0] = __ldg(p + col);
   }
+}
+template <int VEC>
+__device__ __forceinline__ void fast_decode(const FastOperand& o, const uint32_t (&raw)[VEC], float (&v)[VEC]) {
+  if (o.kind == K_IMM) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) v[j] = o.imm;
+  } else if (o.kind == K_F32) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) v[j] = __uint_as_float(o.s0 ? raw[j] : raw[0]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) v[j] = (float)(o.s0 ? ((raw[0] >> (8 * j)) & 0xffu) : raw[0]);
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void fast_load(const FastOperand& o, uint32_t i2, uint32_t i1,
+                                          uint32_t col, float (&v)[VEC]) {
+  uint32_t raw[VEC] = {};
+  fast_load_raw<VEC>(o, i2, i1, col, raw);
+  fast_decode<VEC>(o, raw, v);
 }
 
 // ---- host-side shape analysis shared by elementwise / reduce -----------------------------------

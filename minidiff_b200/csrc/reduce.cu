@@ -66,23 +66,42 @@ __device__ __forceinline__ void load_apply(const RedParams& p, uint32_t i2, uint
     r[j] = apply<OP, float>(v[0][j], NIN > 1 ? v[1][j] : 0.f, NIN > 2 ? v[2][j] : 0.f, p.aux);
 }
 
-// U items: all loads first, then the elementwise functor (keeps U*NIN loads in flight per thread)
-template <int OP, int NIN, int VEC, int U>
-__device__ __forceinline__ void load_then_apply(const RedParams& p, const uint32_t (&i2)[U], const uint32_t (&i1)[U],
-                                                const uint32_t (&col)[U], const bool (&ok)[U], float (&r)[U][VEC]) {
-  float v[U][3][VEC];
+// U items in two phases: every load of the thread is issued before anything depends on one
+// (fast_load_raw keeps raw bits only), then decode -> elementwise functor -> fold into acc.
+// LATE: operands 1.. are small (immediates, scalars, row / column vectors that live in L1/L2), so
+// only operand 0 is streamed through the raw registers and the others are read at fold time; the
+// registers saved buy another resident CTA per SM (ncu: the fused gradient sums sat at 33 %
+// occupancy and 0.5-0.6 of the HBM roofline with every operand staged).
+// (Tried and dropped: hoisting each operand's (kind, stride) decode into per-thread state -- the
+// extra live registers and the 5-way mode select made both fused forms slower, 0.54 / 0.40.)
+template <int NIN, int VEC, int U, bool LATE>
+__device__ __forceinline__ void load_phase(const RedParams& p, const uint32_t (&i2)[U], const uint32_t (&i1)[U],
+                                           const uint32_t (&col)[U], const bool (&ok)[U],
+                                           uint32_t (&raw)[U][LATE ? 1 : NIN][VEC]) {
 #pragma unroll
   for (int u = 0; u < U; ++u)
     if (ok[u]) {
 #pragma unroll
-      for (int k = 0; k < NIN; ++k) fast_load<VEC>(p.in[k], i2[u], i1[u], col[u], v[u][k]);
+      for (int k = 0; k < (LATE ? 1 : NIN); ++k) fast_load_raw<VEC>(p.in[k], i2[u], i1[u], col[u], raw[u][k]);
     }
+}
+template <int OP, int NIN, int RED, int VEC, int U, bool LATE>
+__device__ __forceinline__ void fold_phase(const RedParams& p, const uint32_t (&i2)[U], const uint32_t (&i1)[U],
+                                           const uint32_t (&col)[U], const bool (&ok)[U],
+                                           const uint32_t (&raw)[U][LATE ? 1 : NIN][VEC], float (&acc)[VEC]) {
 #pragma unroll
   for (int u = 0; u < U; ++u)
     if (ok[u]) {
+      float v[3][VEC];
+#pragma unroll
+      for (int k = 0; k < NIN; ++k) {
+        if (LATE && k > 0) fast_load<VEC>(p.in[k], i2[u], i1[u], col[u], v[k]);
+        else fast_decode<VEC>(p.in[k], raw[u][LATE ? 0 : k], v[k]);
+      }
 #pragma unroll
       for (int j = 0; j < VEC; ++j)
-        r[u][j] = apply<OP, float>(v[u][0][j], NIN > 1 ? v[u][1][j] : 0.f, NIN > 2 ? v[u][2][j] : 0.f, p.aux);
+        acc[j] = red_combine<RED>(acc[j], apply<OP, float>(v[0][j], NIN > 1 ? v[1][j] : 0.f,
+                                                           NIN > 2 ? v[2][j] : 0.f, p.aux));
     }
 }
 
@@ -117,8 +136,8 @@ __global__ void __launch_bounds__(256) red_row_warp(const RedParams p) {
 }
 
 // one CTA per (row, split): long rows
-template <int OP, int NIN, int RED, int VEC>
-__global__ void __launch_bounds__(256) red_row_cta(const RedParams p) {
+template <int OP, int NIN, int RED, int VEC, bool LATE = false>
+__global__ void __launch_bounds__(256, NIN == 1 ? 6 : (LATE ? 5 : (NIN == 2 ? 4 : 2))) red_row_cta(const RedParams p) {
   constexpr int U = 4;
   __shared__ float sm[8];
   const uint32_t row = blockIdx.x, split = blockIdx.y;
@@ -130,18 +149,13 @@ __global__ void __launch_bounds__(256) red_row_cta(const RedParams p) {
 #pragma unroll
   for (int j = 0; j < VEC; ++j) acc[j] = red_identity<RED>();
   for (uint32_t c = start + threadIdx.x; c < end; c += 256 * U) {
-    float r[U][VEC];
+    uint32_t raw[U][LATE ? 1 : NIN][VEC];
     uint32_t a2[U], a1[U], cc[U];
     bool ok[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) { a2[u] = i2; a1[u] = i1; cc[u] = (c + u * 256) * VEC; ok[u] = c + u * 256 < end; }
-    load_then_apply<OP, NIN, VEC, U>(p, a2, a1, cc, ok, r);
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (c + u * 256 < end) {
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) acc[j] = red_combine<RED>(acc[j], r[u][j]);
-      }
+    load_phase<NIN, VEC, U, LATE>(p, a2, a1, cc, ok, raw);
+    fold_phase<OP, NIN, RED, VEC, U, LATE>(p, a2, a1, cc, ok, raw, acc);
   }
   float a = acc[0];
   if constexpr (VEC == 4)
@@ -160,8 +174,8 @@ __global__ void __launch_bounds__(256) red_row_cta(const RedParams p) {
 }
 
 // reduce over collapsed dim 1 (rows), keep dim 2 (outer) and dim 0 (inner, contiguous)
-template <int OP, int NIN, int RED, int VEC>
-__global__ void __launch_bounds__(256) red_col(const RedParams p) {
+template <int OP, int NIN, int RED, int VEC, bool LATE = false>
+__global__ void __launch_bounds__(256, NIN == 1 ? 6 : (LATE ? 5 : (NIN == 2 ? 4 : 2))) red_col(const RedParams p) {
   constexpr int U = 4;
   __shared__ float sm[8][32][VEC];
   const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -174,18 +188,13 @@ __global__ void __launch_bounds__(256) red_col(const RedParams p) {
   for (int j = 0; j < VEC; ++j) acc[j] = red_identity<RED>();
   if (active) {
     for (uint32_t r = r0 + ty; r < r1; r += 8 * U) {
-      float v[U][VEC];
+      uint32_t raw[U][LATE ? 1 : NIN][VEC];
       uint32_t a2[U], a1[U], cc[U];
       bool ok[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) { a2[u] = o2; a1[u] = r + u * 8; cc[u] = col; ok[u] = r + u * 8 < r1; }
-      load_then_apply<OP, NIN, VEC, U>(p, a2, a1, cc, ok, v);
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (r + u * 8 < r1) {
-#pragma unroll
-          for (int j = 0; j < VEC; ++j) acc[j] = red_combine<RED>(acc[j], v[u][j]);
-        }
+      load_phase<NIN, VEC, U, LATE>(p, a2, a1, cc, ok, raw);
+      fold_phase<OP, NIN, RED, VEC, U, LATE>(p, a2, a1, cc, ok, raw, acc);
     }
   }
 #pragma unroll
@@ -341,6 +350,15 @@ template <int OP, int NIN, int RED>
 static int launch_fast_red(const RedPlan& pl, RedParams p, int vec, float* out, bool accumulate,
                            float divisor) {
   p.accumulate = accumulate; p.divisor = divisor;
+  // LATE kernels: operand 0 streams, every other operand has a footprint of at most 64 KB
+  bool late = NIN > 1;
+  for (int k = 1; k < NIN; ++k) {
+    if (p.in[k].kind == K_IMM) continue;
+    int64_t foot = 1;
+    const int64_t ext[3] = {pl.d2, pl.d1, pl.d0};
+    for (int j = 0; j < 3; ++j) if (pl.istr[k][j] != 0) foot *= ext[j];
+    late = late && foot <= 16384;
+  }
   if (pl.pattern == 0) {
     const int64_t rows = pl.d2 * pl.d1;
     const uint32_t L = (uint32_t)(pl.d0 / vec);
@@ -356,7 +374,7 @@ static int launch_fast_red(const RedPlan& pl, RedParams p, int vec, float* out, 
     }
     // long rows: split so that >= ~4 CTAs per SM exist, each split >= 4096 work items
     // many short CTAs (like the 8192-row axis=1 case, 0.94 of peak) beat few long ones
-    int64_t want = ((int64_t)g_sm_count * 32 + rows - 1) / rows;
+    int64_t want = ((int64_t)g_sm_count * 56 + rows - 1) / rows;   // ~9 waves of 2-iteration CTAs: short tail
     int64_t maxsplit = std::max<int64_t>(1, L / 2048);
     uint32_t nsplit = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(std::min(want, maxsplit), 65535));
     uint32_t seg = (L + nsplit - 1) / nsplit;
@@ -370,8 +388,12 @@ static int launch_fast_red(const RedPlan& pl, RedParams p, int vec, float* out, 
       p.dst = out; p.to_partial = 0;
     }
     dim3 grid((unsigned)rows, nsplit);
-    if (vec == 4) red_row_cta<OP, NIN, RED, 4><<<grid, 256, 0, g_stream>>>(p);
-    else red_row_cta<OP, NIN, RED, 1><<<grid, 256, 0, g_stream>>>(p);
+    if (vec == 4) {
+      if (NIN > 1 && late) red_row_cta<OP, NIN, RED, 4, (NIN > 1)><<<grid, 256, 0, g_stream>>>(p);
+      else red_row_cta<OP, NIN, RED, 4><<<grid, 256, 0, g_stream>>>(p);
+    } else {
+      red_row_cta<OP, NIN, RED, 1><<<grid, 256, 0, g_stream>>>(p);
+    }
     MDB_CHECK_LAUNCH();
     if (nsplit > 1) {  // second pass over the [rows, nsplit] partials
       RedParams q = p;
@@ -394,7 +416,7 @@ static int launch_fast_red(const RedPlan& pl, RedParams p, int vec, float* out, 
   p.L = (uint32_t)R; p.I = (uint32_t)I; p.os2 = pl.ostr[0];
   const int tile = 32 * vec;
   const int64_t gx = (I + tile - 1) / tile;
-  int64_t want = ((int64_t)g_sm_count * 8 + gx * O2 - 1) / (gx * O2);
+  int64_t want = ((int64_t)g_sm_count * 24 + gx * O2 - 1) / (gx * O2);   // ~4 full waves (8 CTAs/SM gave 1.37 waves: 27 % tail)
   int64_t maxsplit = std::max<int64_t>(1, R / 64);
   uint32_t nsplit = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(std::min(want, maxsplit), 1024));
   if ((int64_t)nsplit * I * O2 >= (int64_t(1) << 31)) nsplit = 1;
@@ -409,8 +431,12 @@ static int launch_fast_red(const RedPlan& pl, RedParams p, int vec, float* out, 
     p.dst = out; p.to_partial = 0;
   }
   dim3 grid((unsigned)gx, nsplit, (unsigned)O2);
-  if (vec == 4) red_col<OP, NIN, RED, 4><<<grid, 256, 0, g_stream>>>(p);
-  else red_col<OP, NIN, RED, 1><<<grid, 256, 0, g_stream>>>(p);
+  if (vec == 4) {
+    if (NIN > 1 && late) red_col<OP, NIN, RED, 4, (NIN > 1)><<<grid, 256, 0, g_stream>>>(p);
+    else red_col<OP, NIN, RED, 4><<<grid, 256, 0, g_stream>>>(p);
+  } else {
+    red_col<OP, NIN, RED, 1><<<grid, 256, 0, g_stream>>>(p);
+  }
   MDB_CHECK_LAUNCH();
   if (nsplit > 1) {
     RedParams q = p;
