@@ -427,6 +427,49 @@ def bench_c3(dev, steps, warmup, peaks, n=8192):
                          "note": "peak = half the measured burst bf16 rate; 3xTF32 pipe use = 3*frac"}}
 
 
+def bench_c1(dev, iters=200):
+    """BASELINE config 1 (latency-bound, no roofline): README example on 2x4 tensors, first- and
+    second-order backward; eager (one Python call + launch per op) vs one CUDA-graph replay."""
+    md = dev.md
+    x = md.Tensor([[0, 2, -2, 1], [-1, -1, -2, -2]], allow_grad=True, dtype=md.float32)
+    y = md.Tensor([[2, 3, 4, 5], [0, -1, -3, 2]], allow_grad=True, dtype=md.float32)
+
+    def step():
+        f = 2 * y * md.sin(x) - x ** 2
+        f.backward(allow_higher_order=True)
+        x.grad.backward()
+        return f
+
+    for _ in range(5):
+        step()
+    dev.sync()
+    l0 = dev.launches()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        step()
+    dev.sync()
+    eager_us = (time.perf_counter() - t0) * 1e6 / iters
+    launches = (dev.launches() - l0) / iters
+    g = md.capture_graph(step)
+    g.replay()
+    dev.sync()
+    e0, e1 = dev.event(), dev.event()
+    t0 = time.perf_counter()
+    dev.record(e0)
+    for _ in range(iters):
+        g.replay()
+    dev.record(e1)
+    dev.sync()
+    graph_wall_us = (time.perf_counter() - t0) * 1e6 / iters
+    graph_dev_us = dev.elapsed_ms(e0, e1) * 1e3 / iters
+    d2 = x.grad.as_numpy().ravel().tolist()
+    g.close()
+    return {"workload": "C1 f = 2*y*sin(x) - x**2 on 2x4 fp32, backward(allow_higher_order) + x.grad.backward()",
+            "launches_per_iter": launches, "eager_us_per_iter": eager_us,
+            "graph_replay_us_per_iter": graph_wall_us, "graph_replay_device_us_per_iter": graph_dev_us,
+            "d2f_dx2": d2}
+
+
 def bench_c5(dev, steps, warmup, peaks, batch=8192):
     """BASELINE config 5: Hessian-vector product through a second-order graph of device ops."""
     md = dev.md
@@ -542,7 +585,8 @@ def main():
     line["warmup"] = warmup
     if rank == 0 and world == 1:
         if not args.skip_extras:
-            line["fwd_bwd"] = {"c2_broadcast_chain": bench_c2(dev, max(args.steps, 10), warmup, peaks),
+            line["fwd_bwd"] = {"c1_readme": bench_c1(dev),
+                               "c2_broadcast_chain": bench_c2(dev, max(args.steps, 10), warmup, peaks),
                                "c3_matmul": bench_c3(dev, max(2, min(args.steps, 5)), warmup, peaks),
                                "c5_hvp": bench_c5(dev, max(args.steps, 10), warmup, peaks)}
         if not args.skip_cpu:

@@ -123,6 +123,17 @@ int mdb_event_record(void* ev);
 int mdb_event_elapsed_ms(void* start, void* stop, float* ms);  /* syncs on `stop`                 */
 int mdb_event_destroy(void* ev);
 uint64_t mdb_launch_count(void);                  /* kernels launched by this library so far     */
+/* CUDA graphs -- the device-side counterpart of the reference's caching.reuse_graph
+ * (caching.py:15-65, topology.py:152-162: "this graph repeats, do the bookkeeping once").  Everything
+ * launched on the compute stream between begin and end is captured; mdb_graph_launch replays it with
+ * one launch.  Memory handed out while capturing is pinned to the graph (private pool) until
+ * mdb_graph_destroy, so replays always find their buffers.  A capture must not synchronise, read back
+ * (mdb_d2h) or upload (mdb_h2d); the profiler must be off. */
+int mdb_graph_begin(void);
+int mdb_graph_end(void** graph);
+int mdb_graph_launch(void* graph);
+int mdb_graph_info(void* graph, uint64_t* kernel_launches, size_t* pinned_bytes);
+int mdb_graph_destroy(void* graph);
 /* per-class device time of the library's own launches, measured with CUDA event pairs on the
  * compute stream around each public compute call while enabled.  cls: 0 elementwise (incl. copy /
  * fill), 1 reductions (incl. the fused un-broadcast form), 2 GEMM, 3 other.  `work` is the summed

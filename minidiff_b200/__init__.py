@@ -15,5 +15,6 @@ from .topology import OpNode  # noqa: F401,E402
 from .ops.wrapping import *  # noqa: F401,F403,E402
 from .ops.definitions import *  # noqa: F401,F403,E402
 from .caching import reuse_graph  # noqa: F401,E402
+from .graphs import CapturedGraph, capture_graph  # noqa: F401,E402
 
 __version__ = "0.1.0"

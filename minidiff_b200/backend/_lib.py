@@ -79,6 +79,11 @@ _SIGS = {
     "mdb_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_void_p, _P(C.c_float)]),
     "mdb_event_destroy": (C.c_int, [C.c_void_p]),
     "mdb_launch_count": (C.c_uint64, []),
+    "mdb_graph_begin": (C.c_int, []),
+    "mdb_graph_end": (C.c_int, [_P(C.c_void_p)]),
+    "mdb_graph_launch": (C.c_int, [C.c_void_p]),
+    "mdb_graph_info": (C.c_int, [C.c_void_p, _P(C.c_uint64), _P(C.c_size_t)]),
+    "mdb_graph_destroy": (C.c_int, [C.c_void_p]),
     "mdb_prof_enable": (C.c_int, [C.c_int]),
     "mdb_prof_read": (C.c_int, [C.c_int, _P(C.c_double), _P(C.c_uint64), _P(C.c_double)]),
     "mdb_fill": (C.c_int, [_A, C.c_double]),

@@ -39,9 +39,24 @@ int ensure_init() {
 // safe without events because every consumer runs on the single compute stream (stream order ==
 // program order); the comm stream only touches buffers between mdb_comm_allreduce_* and
 // mdb_comm_wait, during which the frontend keeps them alive.
+// CUDA-graph capture (mdb_graph_*): a captured graph replays the SAME addresses, so every block that
+// is handed out while a capture is open is tagged with that graph's private pool: when released --
+// during the capture or any time later -- it returns to the pool, never to the general cache, until
+// the graph is destroyed.  Temporaries are therefore recycled inside one capture exactly as they
+// are in eager mode, and nothing outside the graph can be given memory the graph writes on replay.
+struct GraphPool {
+  std::map<size_t, std::vector<void*>> free_lists;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  uint64_t launches = 0;     // kernel launches recorded while capturing (added per replay)
+  size_t bytes = 0;          // device memory pinned by this graph
+};
+
 struct Allocator {
   std::map<size_t, std::vector<void*>> free_lists;
   std::unordered_map<void*, size_t> live;
+  std::unordered_map<void*, GraphPool*> owner;   // blocks (live or pooled) that belong to a graph
+  GraphPool* capturing = nullptr;
   size_t in_use = 0, cached = 0, peak = 0;
   uint64_t n_device_allocs = 0;
 
@@ -50,8 +65,25 @@ struct Allocator {
     if (b <= (1u << 20)) return (b + 511) & ~size_t(511);           // 512 B classes below 1 MiB
     return (b + ((2u << 20) - 1)) & ~size_t((2u << 20) - 1);        // 2 MiB classes above
   }
+  static bool take(std::map<size_t, std::vector<void*>>& lists, size_t& r, void** out) {
+    auto it = lists.lower_bound(r);
+    while (it != lists.end() && it->second.empty()) ++it;
+    if (it != lists.end() && (it->first == r || (r >= (8u << 20) && it->first <= r + r / 2))) {
+      r = it->first;
+      *out = it->second.back();
+      it->second.pop_back();
+      return true;
+    }
+    return false;
+  }
   int alloc(size_t bytes, void** out) {
     size_t r = round(bytes);
+    if (capturing && take(capturing->free_lists, r, out)) {     // recycled inside this graph
+      live[*out] = r;
+      in_use += r;
+      if (in_use > peak) peak = in_use;
+      return 0;
+    }
     // exact class first, then the smallest cached block within 1.5x (large blocks only): a
     // cudaMalloc is a device-wide synchronisation and costs milliseconds at GB sizes
     auto it = free_lists.lower_bound(r);
@@ -85,6 +117,7 @@ struct Allocator {
     live[*out] = r;
     in_use += r;
     if (in_use > peak) peak = in_use;
+    if (capturing) { owner[*out] = capturing; capturing->bytes += r; }
     return 0;
   }
   int free(void* p) {
@@ -93,9 +126,22 @@ struct Allocator {
     size_t r = it->second;
     live.erase(it);
     in_use -= r;
+    auto ow = owner.find(p);
+    if (ow != owner.end()) {                 // graph memory goes back to its graph only
+      ow->second->free_lists[r].push_back(p);
+      return 0;
+    }
     cached += r;
     free_lists[r].push_back(p);
     return 0;
+  }
+  // the graph is gone: its pooled blocks join the general cache, its live blocks become ordinary
+  void dissolve(GraphPool* g) {
+    for (auto& kv : g->free_lists)
+      for (void* p : kv.second) { owner.erase(p); free_lists[kv.first].push_back(p); cached += kv.first; }
+    g->free_lists.clear();
+    for (auto it = owner.begin(); it != owner.end();)
+      if (it->second == g) it = owner.erase(it); else ++it;
   }
   void release_cached() {
     if (g_stream) cudaStreamSynchronize(g_stream);
@@ -323,6 +369,76 @@ int mdb_event_destroy(void* ev) {
   return 0;
 }
 uint64_t mdb_launch_count(void) { return g_launches.load(); }
+
+// ---- CUDA graphs: capture everything the frontend launches on the compute stream between begin
+// and end, replay it with one launch (the device-side counterpart of caching.reuse_graph)
+int mdb_graph_begin(void) {
+  MDB_TRY(ensure_init());
+  std::lock_guard<std::mutex> lk(g_mu);
+  MDB_REQUIRE(g_alloc.capturing == nullptr, "a graph capture is already open");
+  MDB_REQUIRE(!g_prof_on, "switch the profiler off before capturing (timed events cannot be captured)");
+  GraphPool* g = new GraphPool();
+  cudaError_t e = cudaStreamBeginCapture(g_stream, cudaStreamCaptureModeRelaxed);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    delete g;
+    return set_error(MDB_ECUDA, "cudaStreamBeginCapture: %s", cudaGetErrorString(e));
+  }
+  g->launches = g_launches.load();
+  g_alloc.capturing = g;
+  return 0;
+}
+
+int mdb_graph_end(void** out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  GraphPool* g = g_alloc.capturing;
+  MDB_REQUIRE(g != nullptr && out != nullptr, "no graph capture is open");
+  g_alloc.capturing = nullptr;
+  g->launches = g_launches.load() - g->launches;
+  cudaError_t e = cudaStreamEndCapture(g_stream, &g->graph);
+  if (e == cudaSuccess) e = cudaGraphInstantiate(&g->exec, g->graph, 0);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    if (g->graph) cudaGraphDestroy(g->graph);
+    g_alloc.dissolve(g);
+    delete g;
+    return set_error(MDB_ECUDA, "graph capture failed: %s (a capture must not synchronise, read "
+                     "results back or upload from pageable memory)", cudaGetErrorString(e));
+  }
+  *out = (void*)g;
+  return 0;
+}
+
+int mdb_graph_launch(void* graph) {
+  GraphPool* g = (GraphPool*)graph;
+  MDB_REQUIRE(g && g->exec, "invalid graph handle");
+  MDB_REQUIRE(g_alloc.capturing == nullptr, "cannot replay a graph while another capture is open");
+  MDB_CUDA(cudaGraphLaunch(g->exec, g_stream));
+  count_launches((int)g->launches);
+  return 0;
+}
+
+int mdb_graph_info(void* graph, uint64_t* kernel_launches, size_t* pinned_bytes) {
+  GraphPool* g = (GraphPool*)graph;
+  MDB_REQUIRE(g && g->exec, "invalid graph handle");
+  if (kernel_launches) *kernel_launches = g->launches;
+  if (pinned_bytes) *pinned_bytes = g->bytes;
+  return 0;
+}
+
+int mdb_graph_destroy(void* graph) {
+  GraphPool* g = (GraphPool*)graph;
+  if (!g) return 0;
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_device >= 0) {
+    cudaStreamSynchronize(g_stream);
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    g_alloc.dissolve(g);
+  }
+  delete g;
+  return 0;
+}
 
 int mdb_prof_enable(int on) {
   MDB_TRY(ensure_init());

@@ -463,3 +463,75 @@ def test_host_batch_feeder_pipeline_matches_resident_inputs(md):
         assert float(l_ref.item()) == float(l_got.item())
     for a, b in zip(ref, got):
         np.testing.assert_array_equal(a.as_numpy(), b.as_numpy())
+
+
+# ---------------------------------------------------------------- CUDA-graph capture
+def test_captured_graph_replays_c1_with_refreshed_inputs(md):
+    """Capture forward + first-order backward of the README expression once, then replay it on new
+    input values written IN PLACE: results must equal an eager evaluation bit for bit."""
+    rng = np.random.default_rng(3)
+    x = md.Tensor(rng.standard_normal((2, 4)).astype(np.float32), allow_grad=True)
+    y = md.Tensor(rng.standard_normal((2, 4)).astype(np.float32), allow_grad=True)
+
+    def step():
+        f = 2 * y * md.sin(x) - x ** 2
+        f.backward()
+        return f
+
+    g = md.capture_graph(step)
+    assert g.kernel_launches >= 5
+    for seed in (10, 11):
+        xn = np.random.default_rng(seed).standard_normal((2, 4)).astype(np.float32)
+        yn = np.random.default_rng(seed + 100).standard_normal((2, 4)).astype(np.float32)
+        with md.no_grad():               # leaves that already sit in a graph refuse in-place writes
+            x[...] = xn                  # (reference tensor.py:257-264) unless grad tracking is off
+            y[...] = yn
+        f = g.replay()
+        got = (f.as_numpy().copy(), x.grad.as_numpy().copy(), y.grad.as_numpy().copy())
+        xe, ye = md.Tensor(xn, allow_grad=True), md.Tensor(yn, allow_grad=True)
+        fe = 2 * ye * md.sin(xe) - xe ** 2
+        fe.backward()
+        np.testing.assert_array_equal(got[0], fe.as_numpy())
+        np.testing.assert_array_equal(got[1], xe.grad.as_numpy())
+        np.testing.assert_array_equal(got[2], ye.grad.as_numpy())
+    g.close()
+
+
+def test_captured_training_step_matches_eager_and_pins_its_memory(md):
+    """K replays of a captured MLP training step == K eager steps; memory allocated by OTHER work
+    between replays never aliases the graph's buffers (private pool)."""
+    from minidiff_b200 import workloads as W
+
+    dims, B, K = (64, 128, 128, 32), 256, 4
+    X_np, Y_np = W.mlp_data(B, dims[0], dims[-1], seed=5)
+    init = W.mlp_params(dims)
+    X, Y = md.Tensor(X_np), md.Tensor(Y_np)
+    eager = [md.Tensor(p.copy(), allow_grad=True) for p in init]
+    # warmup=0 so that the captured parameters see exactly K updates
+    graph_params = [md.Tensor(p.copy(), allow_grad=True) for p in init]
+    W.mlp_train_step(X, Y, [md.Tensor(p.copy(), allow_grad=True) for p in init])   # first-launch setup
+    g = md.capture_graph(lambda: W.mlp_train_step(X, Y, graph_params), warmup=0)
+    losses = []
+    for _ in range(K):
+        loss = g.replay()
+        junk = [md.backend.ones((257, 129)) * 3.0 for _ in range(8)]   # churn the general allocator
+        del junk
+        losses.append(float(loss.item()))
+    want = [float(W.mlp_train_step(X, Y, eager).item()) for _ in range(K)]
+    np.testing.assert_array_equal(np.float32(losses), np.float32(want))
+    for a, b in zip(graph_params, eager):
+        np.testing.assert_array_equal(a.as_numpy(), b.as_numpy())
+    assert g.pinned_bytes > 0
+    g.close()
+
+
+def test_capture_refuses_readbacks(md):
+    x = md.Tensor(np.ones((4, 4), np.float32), allow_grad=True)
+
+    def bad():
+        return float(md.sum(x * x).item())        # a read-back inside the capture
+
+    with pytest.raises(RuntimeError):
+        md.capture_graph(bad, warmup=1)
+    # the library is usable again afterwards
+    np.testing.assert_allclose(md.sum(x * x).item(), 16.0)
