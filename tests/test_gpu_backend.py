@@ -394,3 +394,22 @@ def test_allocator_reuses_blocks(B):
         y = B.ones((1 << 20,), dtype=np.float32)
         del y
     assert stats()[3] == n0, "freed blocks must be served from the cache, not cudaMalloc"
+
+
+def test_exp_fp32_full_range_and_special_values(B):
+    """exp is evaluated in fp32 arithmetic only (HBM-bound instead of FP64-pipe bound): within 1 ulp
+    of the correctly rounded result over the whole range, including subnormal results, overflow to
+    inf, and the special values NumPy defines."""
+    rng = np.random.default_rng(7)
+    x = np.concatenate([rng.uniform(-104.5, 89.0, 1 << 18), rng.uniform(-1, 1, 1 << 16),
+                        rng.uniform(-103.98, -87.3, 1 << 14), rng.uniform(88.0, 88.73, 1 << 12)]).astype(np.float32)
+    got = host(B.exp(dev(B, x)))
+    with np.errstate(over="ignore", under="ignore"):
+        truth = np.exp(x.astype(np.float64)).astype(np.float32)
+    assert ulp_diff(got, truth).max() <= 1
+    sp = np.array([np.inf, -np.inf, np.nan, 0.0, -0.0, 88.73, 89.0, 200.0, -104.0, -200.0, 1.0, -1.0], np.float32)
+    g = host(B.exp(dev(B, sp)))
+    with np.errstate(over="ignore", under="ignore"):
+        w = np.exp(sp)
+    assert np.isnan(g[2]) and g[0] == np.inf and g[1] == 0.0 and g[3] == 1.0 and g[4] == 1.0
+    assert ulp_diff(np.nan_to_num(g, nan=0.0, posinf=3e38), np.nan_to_num(w, nan=0.0, posinf=3e38)).max() <= 2
