@@ -213,6 +213,130 @@ __global__ void __launch_bounds__(256, NIN == 1 ? 6 : (LATE ? 5 : (NIN == 2 ? 4 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Form-specialised fp32 kernels (<= 2 operands, 128-bit vectors).  ncu on the generic kernels above:
+// sum(t*c, axis=1) and sum(t*a, axis=0) executed ~95 warp instructions per float4 item (runtime
+// kind / stride decode, 64-bit offset math per operand per item) and were ISSUE-bound (issue slots
+// 72-78 % busy) at 0.62-0.64 of the HBM roofline, while the plain sum needs 36.  Here the access
+// form of every operand is a template parameter, so the inner loop is loads + math only:
+//   FV  unit-stride fp32 vector (row kernel: along the row; col kernel: 4 adjacent columns, any row pitch)
+//   FK  constant for the whole thread (immediate, or a scalar that does not move along the reduced axis)
+//   FS  col kernel only: one fp32 scalar per reduced row (e.g. a (N,1) column against (N,M) data)
+enum { FV = 0, FK = 1, FS = 2 };
+
+template <int F>
+__device__ __forceinline__ float4 form_value(const float4& v, float k) {
+  if constexpr (F == FV) return v;
+  else return make_float4(k, k, k, k);
+}
+template <int OP, int NIN, int RED>
+__device__ __forceinline__ void fold4(const RedParams& p, const float4& a, const float4& b, float (&acc)[4]) {
+  acc[0] = red_combine<RED>(acc[0], apply<OP, float>(a.x, NIN > 1 ? b.x : 0.f, 0.f, p.aux));
+  acc[1] = red_combine<RED>(acc[1], apply<OP, float>(a.y, NIN > 1 ? b.y : 0.f, 0.f, p.aux));
+  acc[2] = red_combine<RED>(acc[2], apply<OP, float>(a.z, NIN > 1 ? b.z : 0.f, 0.f, p.aux));
+  acc[3] = red_combine<RED>(acc[3], apply<OP, float>(a.w, NIN > 1 ? b.w : 0.f, 0.f, p.aux));
+}
+__device__ __forceinline__ float const_of(const FastOperand& o, int64_t off) {
+  return o.kind == K_IMM ? o.imm : __ldg((const float*)o.ptr + off);
+}
+
+template <int OP, int NIN, int RED, int F0, int F1>
+__global__ void __launch_bounds__(256, (NIN == 2 && F0 == FV && F1 == FV) ? 5 : 6) red_row_f32(const RedParams p) {
+  constexpr int U = 4;
+  __shared__ float sm[8];
+  const uint32_t row = blockIdx.x, split = blockIdx.y;
+  uint32_t i2, i1;
+  p.div_d1.divmod(row, i2, i1);
+  const uint32_t start = split * p.seg;
+  const uint32_t end = min(start + p.seg, p.L);
+  const int64_t off0 = (int64_t)(int32_t)i2 * p.in[0].s2 + (int64_t)(int32_t)i1 * p.in[0].s1;
+  const int64_t off1 = NIN > 1 ? (int64_t)(int32_t)i2 * p.in[1].s2 + (int64_t)(int32_t)i1 * p.in[1].s1 : 0;
+  const float4* b0 = F0 == FV ? (const float4*)((const float*)p.in[0].ptr + off0) : nullptr;
+  const float4* b1 = (NIN > 1 && F1 == FV) ? (const float4*)((const float*)p.in[1].ptr + off1) : nullptr;
+  const float k0 = F0 == FK ? const_of(p.in[0], off0) : 0.f;
+  const float k1 = (NIN > 1 && F1 == FK) ? const_of(p.in[1], off1) : 0.f;
+  float acc[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) acc[j] = red_identity<RED>();
+  for (uint32_t c = start + threadIdx.x; c < end; c += 256 * U) {
+    float4 x0[U], x1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (c + u * 256 < end) {
+        if constexpr (F0 == FV) x0[u] = __ldg(b0 + c + u * 256);
+        if constexpr (NIN > 1 && F1 == FV) x1[u] = __ldg(b1 + c + u * 256);
+      }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (c + u * 256 < end) fold4<OP, NIN, RED>(p, form_value<F0>(x0[u], k0), form_value<F1>(x1[u], k1), acc);
+  }
+  float a = red_combine<RED>(red_combine<RED>(acc[0], acc[1]), red_combine<RED>(acc[2], acc[3]));
+  a = warp_reduce<RED>(a);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float b = threadIdx.x < 8 ? sm[threadIdx.x] : red_identity<RED>();
+    b = warp_reduce<RED>(b);
+    if (threadIdx.x == 0) {
+      if (p.to_partial) p.dst[(int64_t)row * p.nsplit + split] = b;
+      else final_store(p, p.dst + (int64_t)i2 * p.os2 + (int64_t)i1 * p.os1, b);
+    }
+  }
+}
+
+template <int OP, int NIN, int RED, int F0, int F1>
+__global__ void __launch_bounds__(256, (NIN == 2 && F0 == FV && F1 == FV) ? 5 : 6) red_col_f32(const RedParams p) {
+  constexpr int U = 4;
+  __shared__ float sm[8][32][4];
+  const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const uint32_t col = (blockIdx.x * 32 + tx) * 4;
+  const uint32_t split = blockIdx.y, o2 = blockIdx.z;
+  const bool active = col < p.I;
+  const uint32_t r0 = split * p.seg, r1 = min(r0 + p.seg, p.L);
+  float acc[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) acc[j] = red_identity<RED>();
+  if (active) {
+    // per-thread bases: vectors start at this thread's 4 columns, scalars at column 0
+    const float* q0 = (const float*)p.in[0].ptr + (int64_t)(int32_t)o2 * p.in[0].s2 + (F0 == FV ? col : 0);
+    const float* q1 = NIN > 1 ? (const float*)p.in[1].ptr + (int64_t)(int32_t)o2 * p.in[1].s2 + (F1 == FV ? col : 0) : nullptr;
+    const int64_t st0 = p.in[0].s1, st1 = NIN > 1 ? p.in[1].s1 : 0;
+    const float k0 = F0 == FK ? const_of(p.in[0], (int64_t)(int32_t)o2 * p.in[0].s2) : 0.f;
+    const float k1 = (NIN > 1 && F1 == FK) ? const_of(p.in[1], (int64_t)(int32_t)o2 * p.in[1].s2) : 0.f;
+    for (uint32_t r = r0 + ty; r < r1; r += 8 * U) {
+      float4 x0[U], x1[U];
+      float s0v[U], s1v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (r + u * 8 < r1) {
+          const int64_t rr = (int64_t)(r + u * 8);
+          if constexpr (F0 == FV) x0[u] = __ldg((const float4*)(q0 + rr * st0));
+          if constexpr (F0 == FS) s0v[u] = __ldg(q0 + rr * st0);
+          if constexpr (NIN > 1 && F1 == FV) x1[u] = __ldg((const float4*)(q1 + rr * st1));
+          if constexpr (NIN > 1 && F1 == FS) s1v[u] = __ldg(q1 + rr * st1);
+        }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (r + u * 8 < r1)
+          fold4<OP, NIN, RED>(p, form_value<F0>(x0[u], F0 == FS ? s0v[u] : k0),
+                              form_value<F1>(x1[u], F1 == FS ? s1v[u] : k1), acc);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) sm[ty][tx][j] = acc[j];
+  __syncthreads();
+  if (ty == 0 && active) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = sm[0][tx][j];
+#pragma unroll
+      for (int t = 1; t < 8; ++t) a = red_combine<RED>(a, sm[t][tx][j]);
+      if (p.to_partial) p.dst[((int64_t)o2 * p.nsplit + split) * p.I + col + j] = a;
+      else final_store(p, p.dst + (int64_t)o2 * p.os2 + col + j, a);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // generic fallback: one thread per output element, any dtype / strides / axes
 // ------------------------------------------------------------------------------------------------
 struct GenRedParams {
@@ -346,10 +470,62 @@ static bool aligned16(const void* p, size_t a) { return ((uintptr_t)p % a) == 0;
   X(MDB_OP_COS_BWD, 2) X(MDB_OP_EXP_BWD, 2) X(MDB_OP_LOG_BWD, 2) X(MDB_OP_RELU_MASK_BWD, 2)     \
   X(MDB_OP_POW_BWD, 3) X(MDB_OP_DIV_BWD_Y, 3) X(MDB_OP_POW_BWD_LIN, 3)
 
+// operand forms for the specialised kernels; returns false when an operand needs the generic path
+static bool classify_forms(const RedPlan& pl, const RedParams& p, int n_in, int (&form)[2]) {
+  if (n_in > 2) return false;
+  form[0] = form[1] = FV;
+  for (int k = 0; k < n_in; ++k) {
+    const FastOperand& o = p.in[k];
+    if (o.kind == K_IMM) { form[k] = FK; continue; }
+    if (o.kind != K_F32) return false;
+    if (o.s0 == 1) form[k] = FV;
+    else if (pl.pattern == 0) form[k] = FK;                    // row kernel: a scalar per row
+    else form[k] = (o.s1 != 0) ? FS : FK;                      // col kernel
+  }
+  if (n_in == 1) return form[0] == FV;
+  return form[0] == FV || form[1] == FV;                       // at least one operand streams
+}
+
+template <int OP, int NIN, int RED>
+static bool launch_row_forms(const int (&f)[2], dim3 grid, const RedParams& p) {
+  if constexpr (NIN == 1) {
+    red_row_f32<OP, 1, RED, FV, FV><<<grid, 256, 0, g_stream>>>(p);
+    return true;
+  } else if constexpr (NIN == 2) {
+    if (f[0] == FV && f[1] == FV) red_row_f32<OP, 2, RED, FV, FV><<<grid, 256, 0, g_stream>>>(p);
+    else if (f[0] == FV && f[1] == FK) red_row_f32<OP, 2, RED, FV, FK><<<grid, 256, 0, g_stream>>>(p);
+    else if (f[0] == FK && f[1] == FV) red_row_f32<OP, 2, RED, FK, FV><<<grid, 256, 0, g_stream>>>(p);
+    else return false;
+    return true;
+  } else {
+    return false;
+  }
+}
+template <int OP, int NIN, int RED>
+static bool launch_col_forms(const int (&f)[2], dim3 grid, const RedParams& p) {
+  if constexpr (NIN == 1) {
+    red_col_f32<OP, 1, RED, FV, FV><<<grid, 256, 0, g_stream>>>(p);
+    return true;
+  } else if constexpr (NIN == 2) {
+    if (f[0] == FV && f[1] == FV) red_col_f32<OP, 2, RED, FV, FV><<<grid, 256, 0, g_stream>>>(p);
+    else if (f[0] == FV && f[1] == FS) red_col_f32<OP, 2, RED, FV, FS><<<grid, 256, 0, g_stream>>>(p);
+    else if (f[0] == FS && f[1] == FV) red_col_f32<OP, 2, RED, FS, FV><<<grid, 256, 0, g_stream>>>(p);
+    else if (f[0] == FV && f[1] == FK) red_col_f32<OP, 2, RED, FV, FK><<<grid, 256, 0, g_stream>>>(p);
+    else if (f[0] == FK && f[1] == FV) red_col_f32<OP, 2, RED, FK, FV><<<grid, 256, 0, g_stream>>>(p);
+    else return false;
+    return true;
+  } else {
+    return false;
+  }
+}
+
 template <int OP, int NIN, int RED>
 static int launch_fast_red(const RedPlan& pl, RedParams p, int vec, float* out, bool accumulate,
                            float divisor) {
   p.accumulate = accumulate; p.divisor = divisor;
+  int form[2];
+  static const bool no_forms = getenv("MDB_RED_GENERIC") != nullptr;       // A/B switch for measurements
+  const bool forms_ok = !no_forms && vec == 4 && classify_forms(pl, p, NIN, form);
   // LATE kernels: operand 0 streams, every other operand has a footprint of at most 64 KB
   bool late = NIN > 1;
   for (int k = 1; k < NIN; ++k) {
@@ -389,7 +565,8 @@ static int launch_fast_red(const RedPlan& pl, RedParams p, int vec, float* out, 
     }
     dim3 grid((unsigned)rows, nsplit);
     if (vec == 4) {
-      if (NIN > 1 && late) red_row_cta<OP, NIN, RED, 4, (NIN > 1)><<<grid, 256, 0, g_stream>>>(p);
+      if (forms_ok && launch_row_forms<OP, NIN, RED>(form, grid, p)) {}
+      else if (NIN > 1 && late) red_row_cta<OP, NIN, RED, 4, (NIN > 1)><<<grid, 256, 0, g_stream>>>(p);
       else red_row_cta<OP, NIN, RED, 4><<<grid, 256, 0, g_stream>>>(p);
     } else {
       red_row_cta<OP, NIN, RED, 1><<<grid, 256, 0, g_stream>>>(p);
@@ -432,7 +609,8 @@ static int launch_fast_red(const RedPlan& pl, RedParams p, int vec, float* out, 
   }
   dim3 grid((unsigned)gx, nsplit, (unsigned)O2);
   if (vec == 4) {
-    if (NIN > 1 && late) red_col<OP, NIN, RED, 4, (NIN > 1)><<<grid, 256, 0, g_stream>>>(p);
+    if (forms_ok && launch_col_forms<OP, NIN, RED>(form, grid, p)) {}
+    else if (NIN > 1 && late) red_col<OP, NIN, RED, 4, (NIN > 1)><<<grid, 256, 0, g_stream>>>(p);
     else red_col<OP, NIN, RED, 4><<<grid, 256, 0, g_stream>>>(p);
   } else {
     red_col<OP, NIN, RED, 1><<<grid, 256, 0, g_stream>>>(p);
