@@ -152,6 +152,65 @@ def test_c3_vs_float64(md, n):
     np.testing.assert_allclose(B.grad.as_numpy(), A64.T @ ones, **tol)
 
 
+def test_c3_full_size_properties(md):
+    """BASELINE size (8192^3, all three GEMMs on the CTA-pair tcgen05 kernel): no CPU recomputation
+    of 1.1 TFLOP; instead (i) a random sample of C entries against float64 dot products,
+    (ii) dA = 1 @ B^T means every row of dA equals the row sums of B, and dB = A^T @ 1 means every
+    column of dB equals the column sums of A -- checked against float64 sums."""
+    n = 8192
+    A_np = np.random.default_rng(1234).standard_normal((n, n), dtype=np.float32)
+    B_np = np.random.default_rng(1235).standard_normal((n, n), dtype=np.float32)
+    A, B = md.Tensor(A_np, allow_grad=True), md.Tensor(B_np, allow_grad=True)
+    C = A @ B
+    C.backward()
+    Cn = C.as_numpy()
+    rng = np.random.default_rng(0)
+    ii, jj = rng.integers(0, n, 256), rng.integers(0, n, 256)
+    truth = np.einsum("sk,ks->s", A_np[ii].astype(np.float64), B_np[:, jj].astype(np.float64))
+    np.testing.assert_allclose(Cn[ii, jj], truth, rtol=1e-4, atol=1e-5 * np.sqrt(n))
+    # a full tile row / column too (catches a wrong tile mapping that a sparse sample could miss)
+    np.testing.assert_allclose(Cn[4097], A_np[4097].astype(np.float64) @ B_np.astype(np.float64),
+                               rtol=1e-4, atol=1e-5 * np.sqrt(n))
+    row_sums_B = B_np.astype(np.float64).sum(axis=1)          # dA[i, k] = sum_j B[k, j]
+    col_sums_A = A_np.astype(np.float64).sum(axis=0)          # dB[k, j] = sum_i A[i, k]
+    dA, dB = A.grad.as_numpy(), B.grad.as_numpy()
+    tol = dict(rtol=1e-4, atol=1e-5 * np.sqrt(n))
+    for i in (0, 127, 128, 4095, 8191):
+        np.testing.assert_allclose(dA[i], row_sums_B, **tol)
+    for j in (0, 255, 256, 5000, 8191):
+        np.testing.assert_allclose(dB[:, j], col_sums_A, **tol)
+    assert np.ptp(dA, axis=0).max() <= 2e-5 * np.sqrt(n) and np.ptp(dB, axis=1).max() <= 2e-5 * np.sqrt(n)
+
+
+def test_c4_full_size_properties(md):
+    """BASELINE size (batch 65536, 1024-4096-4096-1024): the mean-MSE gradient of the full batch is
+    the average of the gradients of its two halves (the identity data parallelism relies on), and
+    the last bias gradient equals 2/(B*1024) * column sums of (out - Y) recomputed with device ops."""
+    from minidiff_b200 import workloads as W
+
+    B = 65536
+    X_np, Y_np = W.mlp_data(B, 1024, 1024, seed=3)
+    init = W.mlp_params()
+
+    def grads_of(Xs, Ys):
+        ps = [md.Tensor(p.copy(), allow_grad=True) for p in init]
+        X, Y = md.Tensor(Xs), md.Tensor(Ys)
+        out = W.mlp_forward(X, ps)
+        loss = md.mean((out - Y) ** 2)
+        loss.backward()
+        resid = md.sum(out - Y, axis=0).as_numpy().astype(np.float64)
+        return float(loss.item()), [p.grad.as_numpy() for p in ps], resid
+
+    l_full, g_full, resid = grads_of(X_np, Y_np)
+    np.testing.assert_allclose(g_full[5], 2.0 * resid / (B * 1024.0), rtol=1e-4, atol=1e-9)
+    l_a, g_a, _ = grads_of(X_np[: B // 2], Y_np[: B // 2])
+    l_b, g_b, _ = grads_of(X_np[B // 2:], Y_np[B // 2:])
+    assert abs(l_full - 0.5 * (l_a + l_b)) <= 1e-5 * abs(l_full)
+    for gf, ga, gb in zip(g_full, g_a, g_b):
+        scale = np.abs(gf).max()
+        np.testing.assert_allclose(gf, 0.5 * (ga + gb), rtol=1e-4, atol=1e-4 * scale)
+
+
 # ------------------------------------------------------------------ C4: MLP training step
 DIMS, BATCH = (16, 32, 32, 8), 64
 
