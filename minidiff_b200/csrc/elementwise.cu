@@ -4,6 +4,7 @@
 //                4 independent loads in flight per thread, grid sized in multiples of the SM count
 //   ew_generic : any dtype / any strides (<=8 dims), one element per thread-iteration
 #include <algorithm>
+#include <cstdlib>
 #include <limits>
 
 #include "ew_ops.cuh"
@@ -178,6 +179,68 @@ __global__ void __launch_bounds__(256, NIN == 1 ? 6 : (NIN == 2 ? 4 : 3)) ew_fas
 }
 
 // ------------------------------------------------------------------------------------------------
+// row kernel for 2-D broadcast forms (fp32, 128-bit vectors, <= 2 operands)
+// ------------------------------------------------------------------------------------------------
+// ew_fast decodes (row, column) with two magic-number divisions and rebuilds every operand offset in
+// 64-bit arithmetic PER ITEM: ~95 warp instructions per float4 item for the outer product
+// (N,1)*(1,M), which made that write-only kernel issue-bound (issue slots 74 % busy) at 0.63 of the
+// HBM roofline.  Here a CTA owns 1024 consecutive float4 items of ONE row, so the row decode, the
+// operand bases and every per-row constant are computed once per thread, and the access form of each
+// operand is a template parameter: FV = unit-stride vector along the row (row pitch may be 0: a
+// broadcast row vector), FK = constant along the row (immediate, or a scalar picked by the row index).
+enum { FV = 0, FK = 1 };
+
+template <int OP, int NIN, int F0, int F1>
+__global__ void __launch_bounds__(256, NIN == 1 ? 6 : 5) ew_rows(const FastParams p, const uint32_t lv) {
+  constexpr int U = 4;
+  const uint32_t row = blockIdx.x;
+  uint32_t i2, i1;
+  p.div_d1.divmod(row, i2, i1);
+  const int64_t off0 = (int64_t)(int32_t)i2 * p.in[0].s2 + (int64_t)(int32_t)i1 * p.in[0].s1;
+  const int64_t off1 = NIN > 1 ? (int64_t)(int32_t)i2 * p.in[1].s2 + (int64_t)(int32_t)i1 * p.in[1].s1 : 0;
+  const float4* b0 = F0 == FV ? (const float4*)((const float*)p.in[0].ptr + off0) : nullptr;
+  const float4* b1 = (NIN > 1 && F1 == FV) ? (const float4*)((const float*)p.in[1].ptr + off1) : nullptr;
+  float k0 = 0.f, k1 = 0.f;
+  if constexpr (F0 == FK) k0 = p.in[0].kind == K_IMM ? p.in[0].imm : __ldg((const float*)p.in[0].ptr + off0);
+  if constexpr (NIN > 1 && F1 == FK) k1 = p.in[1].kind == K_IMM ? p.in[1].imm : __ldg((const float*)p.in[1].ptr + off1);
+  float4* out = (float4*)((float*)p.out + (int64_t)(int32_t)i2 * p.os2 + (int64_t)(int32_t)i1 * p.os1);
+  const uint32_t c0 = blockIdx.y * (256 * U) + threadIdx.x;
+  float4 x0[U], x1[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (c0 + u * 256 < lv) {
+      if constexpr (F0 == FV) x0[u] = __ldg(b0 + c0 + u * 256);
+      if constexpr (NIN > 1 && F1 == FV) x1[u] = __ldg(b1 + c0 + u * 256);
+    }
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (c0 + u * 256 < lv) {
+      const float4 a = F0 == FV ? x0[u] : make_float4(k0, k0, k0, k0);
+      const float4 b = (NIN > 1 && F1 == FV) ? x1[u] : make_float4(k1, k1, k1, k1);
+      float4 r;
+      r.x = apply<OP, float>(a.x, b.x, 0.f, p.aux);
+      r.y = apply<OP, float>(a.y, b.y, 0.f, p.aux);
+      r.z = apply<OP, float>(a.z, b.z, 0.f, p.aux);
+      r.w = apply<OP, float>(a.w, b.w, 0.f, p.aux);
+      out[c0 + u * 256] = r;
+    }
+}
+
+// binary arithmetic + fused backward forms that occur with broadcast operands in the hot paths
+#define MDB_ROW_BINARY_OPS(X)                                                                   \
+  X(MDB_OP_ADD) X(MDB_OP_SUB) X(MDB_OP_MUL) X(MDB_OP_DIV) X(MDB_OP_MAXIMUM) X(MDB_OP_MINIMUM)   \
+  X(MDB_OP_SIN_BWD) X(MDB_OP_COS_BWD) X(MDB_OP_EXP_BWD) X(MDB_OP_LOG_BWD)
+
+template <int OP>
+static bool launch_rows_binary(const FastParams& p, int f0, int f1, dim3 grid, uint32_t lv) {
+  if (f0 == FV && f1 == FV) ew_rows<OP, 2, FV, FV><<<grid, 256, 0, g_stream>>>(p, lv);
+  else if (f0 == FV && f1 == FK) ew_rows<OP, 2, FV, FK><<<grid, 256, 0, g_stream>>>(p, lv);
+  else if (f0 == FK && f1 == FV) ew_rows<OP, 2, FK, FV><<<grid, 256, 0, g_stream>>>(p, lv);
+  else return false;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
 // generic kernel
 // ------------------------------------------------------------------------------------------------
 struct GenOperand {
@@ -346,6 +409,31 @@ int elementwise_impl(int op, const mdb_array* out, int n_in, const mdb_array* in
       p.total = (uint32_t)items;
       p.div_lv = FastDiv((uint32_t)(L / vec));
       p.div_d1 = FastDiv((uint32_t)d1);
+      // 2-D broadcast forms of fp32 binary ops: one CTA per 1024-float4 chunk of a row
+      static const bool no_rows = getenv("MDB_EW_NO_ROWS") != nullptr;      // A/B switch for measurements
+      if (!no_rows && !flat && vec == 4 && !pred && n_in == 2 && L / 4 >= 512 && d2 * d1 < (int64_t(1) << 31) &&
+          (L / 4 + 1023) / 1024 <= 65535) {
+        int form[2];
+        bool ok = true;
+        for (int k = 0; k < 2; ++k) {
+          const FastOperand& o = p.in[k];
+          if (o.kind == K_IMM) form[k] = FK;
+          else if (o.kind != K_F32) ok = false;
+          else form[k] = o.s0 == 1 ? FV : FK;
+        }
+        if (ok && (form[0] == FV || form[1] == FV)) {
+          const uint32_t lv = (uint32_t)(L / 4);
+          dim3 rgrid((unsigned)(d2 * d1), (unsigned)((lv + 1023) / 1024));
+          bool launched = false;
+          switch (op) {
+#define X(OPID) case OPID: launched = launch_rows_binary<OPID>(p, form[0], form[1], rgrid, lv); break;
+            MDB_ROW_BINARY_OPS(X)
+#undef X
+            default: break;
+          }
+          if (launched) { MDB_CHECK_LAUNCH(); return 0; }
+        }
+      }
       const int per_thread = 4;
       int grid = grid_for((items + per_thread - 1) / per_thread, 256);
       switch (op) {
