@@ -53,6 +53,10 @@ struct RedParams {
   int to_partial;          // 1: dst is the partial buffer [.., nsplit, ..]
   int accumulate;          // final write: dst = dst + result
   float divisor;           // > 0: mean -> result / divisor
+  // single-launch split reductions (f32 form kernels): the LAST CTA of a row / column tile to
+  // deposit its partial folds all partials (fixed order: deterministic) and writes the result.
+  unsigned int* tickets;   // self-resetting arrival counters, or nullptr for the two-launch scheme
+  float* final_dst;        // where the last CTA writes (dst is the partial buffer)
 };
 
 template <int OP, int NIN, int VEC>
@@ -254,6 +258,8 @@ __global__ void __launch_bounds__(256, (NIN == 2 && F0 == FV && F1 == FV) ? 5 : 
   const float4* b1 = (NIN > 1 && F1 == FV) ? (const float4*)((const float*)p.in[1].ptr + off1) : nullptr;
   const float k0 = F0 == FK ? const_of(p.in[0], off0) : 0.f;
   const float k1 = (NIN > 1 && F1 == FK) ? const_of(p.in[1], off1) : 0.f;
+  // an operand whose row pitch is zero is re-read by every row: keep it in L1, stream the others past it
+  const bool keep0 = p.in[0].s1 == 0 && p.in[0].s2 == 0, keep1 = NIN > 1 && p.in[1].s1 == 0 && p.in[1].s2 == 0;
   float acc[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) acc[j] = red_identity<RED>();
@@ -262,8 +268,8 @@ __global__ void __launch_bounds__(256, (NIN == 2 && F0 == FV && F1 == FV) ? 5 : 
 #pragma unroll
     for (int u = 0; u < U; ++u)
       if (c + u * 256 < end) {
-        if constexpr (F0 == FV) x0[u] = __ldg(b0 + c + u * 256);
-        if constexpr (NIN > 1 && F1 == FV) x1[u] = __ldg(b1 + c + u * 256);
+        if constexpr (F0 == FV) x0[u] = keep0 ? __ldg(b0 + c + u * 256) : ldg_stream4(b0 + c + u * 256);
+        if constexpr (NIN > 1 && F1 == FV) x1[u] = keep1 ? __ldg(b1 + c + u * 256) : ldg_stream4(b1 + c + u * 256);
       }
 #pragma unroll
     for (int u = 0; u < U; ++u)
@@ -273,12 +279,41 @@ __global__ void __launch_bounds__(256, (NIN == 2 && F0 == FV && F1 == FV) ? 5 : 
   a = warp_reduce<RED>(a);
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = a;
   __syncthreads();
+  __shared__ int s_last;
   if (threadIdx.x < 32) {
     float b = threadIdx.x < 8 ? sm[threadIdx.x] : red_identity<RED>();
     b = warp_reduce<RED>(b);
     if (threadIdx.x == 0) {
-      if (p.to_partial) p.dst[(int64_t)row * p.nsplit + split] = b;
-      else final_store(p, p.dst + (int64_t)i2 * p.os2 + (int64_t)i1 * p.os1, b);
+      s_last = 0;
+      if (p.to_partial) {
+        p.dst[(int64_t)row * p.nsplit + split] = b;
+        if (p.tickets) {
+          __threadfence();
+          s_last = atomicAdd(&p.tickets[row], 1u) == p.nsplit - 1;
+        }
+      } else {
+        final_store(p, p.dst + (int64_t)i2 * p.os2 + (int64_t)i1 * p.os1, b);
+      }
+    }
+  }
+  if (!p.tickets) return;
+  __syncthreads();
+  if (!s_last) return;
+  // last CTA of this row: fold the nsplit partials (strided per thread, then the block tree)
+  __threadfence();
+  const float* part = p.dst + (int64_t)row * p.nsplit;
+  float t = red_identity<RED>();
+  for (uint32_t k = threadIdx.x; k < p.nsplit; k += 256) t = red_combine<RED>(t, __ldcg(part + k));
+  t = warp_reduce<RED>(t);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float b = threadIdx.x < 8 ? sm[threadIdx.x] : red_identity<RED>();
+    b = warp_reduce<RED>(b);
+    if (threadIdx.x == 0) {
+      final_store(p, p.final_dst + (int64_t)i2 * p.os2 + (int64_t)i1 * p.os1, b);
+      p.tickets[row] = 0;                      // ready for the next launch (and for graph replays)
     }
   }
 }
@@ -309,9 +344,9 @@ __global__ void __launch_bounds__(256, (NIN == 2 && F0 == FV && F1 == FV) ? 5 : 
       for (int u = 0; u < U; ++u)
         if (r + u * 8 < r1) {
           const int64_t rr = (int64_t)(r + u * 8);
-          if constexpr (F0 == FV) x0[u] = __ldg((const float4*)(q0 + rr * st0));
+          if constexpr (F0 == FV) x0[u] = st0 ? ldg_stream4((const float4*)(q0 + rr * st0)) : __ldg((const float4*)q0);
           if constexpr (F0 == FS) s0v[u] = __ldg(q0 + rr * st0);
-          if constexpr (NIN > 1 && F1 == FV) x1[u] = __ldg((const float4*)(q1 + rr * st1));
+          if constexpr (NIN > 1 && F1 == FV) x1[u] = st1 ? ldg_stream4((const float4*)(q1 + rr * st1)) : __ldg((const float4*)q1);
           if constexpr (NIN > 1 && F1 == FS) s1v[u] = __ldg(q1 + rr * st1);
         }
 #pragma unroll
@@ -334,6 +369,39 @@ __global__ void __launch_bounds__(256, (NIN == 2 && F0 == FV && F1 == FV) ? 5 : 
       else final_store(p, p.dst + (int64_t)o2 * p.os2 + col + j, a);
     }
   }
+  if (!p.tickets || !p.to_partial) return;
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  const unsigned int tile = o2 * gridDim.x + blockIdx.x;
+  if (threadIdx.x == 0) s_last = atomicAdd(&p.tickets[tile], 1u) == p.nsplit - 1;
+  __syncthreads();
+  if (!s_last) return;
+  // last CTA of this column tile: fold the partial rows of all splits, 8 row groups then the tree
+  __threadfence();
+  float t4[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) t4[j] = red_identity<RED>();
+  if (active) {
+    for (uint32_t k = ty; k < p.nsplit; k += 8) {
+      const float4 v = __ldcg((const float4*)(p.dst + ((int64_t)o2 * p.nsplit + k) * p.I + col));
+      t4[0] = red_combine<RED>(t4[0], v.x); t4[1] = red_combine<RED>(t4[1], v.y);
+      t4[2] = red_combine<RED>(t4[2], v.z); t4[3] = red_combine<RED>(t4[3], v.w);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) sm[ty][tx][j] = t4[j];
+  __syncthreads();
+  if (ty == 0 && active) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = sm[0][tx][j];
+#pragma unroll
+      for (int t = 1; t < 8; ++t) a = red_combine<RED>(a, sm[t][tx][j]);
+      final_store(p, p.final_dst + (int64_t)o2 * p.os2 + col + j, a);
+    }
+  }
+  if (threadIdx.x == 0) p.tickets[tile] = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -470,6 +538,21 @@ static bool aligned16(const void* p, size_t a) { return ((uintptr_t)p % a) == 0;
   X(MDB_OP_COS_BWD, 2) X(MDB_OP_EXP_BWD, 2) X(MDB_OP_LOG_BWD, 2) X(MDB_OP_RELU_MASK_BWD, 2)     \
   X(MDB_OP_POW_BWD, 3) X(MDB_OP_DIV_BWD_Y, 3) X(MDB_OP_POW_BWD_LIN, 3)
 
+// arrival counters for the single-launch split reductions: 64 Ki zero-initialised words, each reset
+// by the CTA that finishes its row / column tile (so launches and CUDA-graph replays never clear them)
+constexpr int64_t kTickets = 65536;
+static unsigned int* ticket_pool() {
+  static unsigned int* pool = nullptr;
+  if (!pool) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(g_stream, &st);
+    if (st != cudaStreamCaptureStatusNone) return nullptr;      // first use inside a capture: two launches
+    if (cudaMalloc(&pool, kTickets * sizeof(unsigned int)) != cudaSuccess) { cudaGetLastError(); pool = nullptr; return nullptr; }
+    cudaMemsetAsync(pool, 0, kTickets * sizeof(unsigned int), g_stream);
+  }
+  return pool;
+}
+
 // operand forms for the specialised kernels; returns false when an operand needs the generic path
 static bool classify_forms(const RedPlan& pl, const RedParams& p, int n_in, int (&form)[2]) {
   if (n_in > 2) return false;
@@ -523,6 +606,7 @@ template <int OP, int NIN, int RED>
 static int launch_fast_red(const RedPlan& pl, RedParams p, int vec, float* out, bool accumulate,
                            float divisor) {
   p.accumulate = accumulate; p.divisor = divisor;
+  p.tickets = nullptr; p.final_dst = nullptr;
   int form[2];
   static const bool no_forms = getenv("MDB_RED_GENERIC") != nullptr;       // A/B switch for measurements
   const bool forms_ok = !no_forms && vec == 4 && classify_forms(pl, p, NIN, form);
@@ -564,15 +648,20 @@ static int launch_fast_red(const RedPlan& pl, RedParams p, int vec, float* out, 
       p.dst = out; p.to_partial = 0;
     }
     dim3 grid((unsigned)rows, nsplit);
+    if (vec == 4 && forms_ok && nsplit > 1 && rows <= kTickets) {
+      p.tickets = ticket_pool();
+      p.final_dst = out;
+    }
+    bool used_forms = false;
     if (vec == 4) {
-      if (forms_ok && launch_row_forms<OP, NIN, RED>(form, grid, p)) {}
+      if (forms_ok && (used_forms = launch_row_forms<OP, NIN, RED>(form, grid, p))) {}
       else if (NIN > 1 && late) red_row_cta<OP, NIN, RED, 4, (NIN > 1)><<<grid, 256, 0, g_stream>>>(p);
       else red_row_cta<OP, NIN, RED, 4><<<grid, 256, 0, g_stream>>>(p);
     } else {
       red_row_cta<OP, NIN, RED, 1><<<grid, 256, 0, g_stream>>>(p);
     }
     MDB_CHECK_LAUNCH();
-    if (nsplit > 1) {  // second pass over the [rows, nsplit] partials
+    if (nsplit > 1 && !(used_forms && p.tickets)) {  // second pass over the [rows, nsplit] partials
       RedParams q = p;
       q.in[0].ptr = tmp.ptr; q.in[0].kind = K_F32; q.in[0].s0 = 1;
       q.in[0].s1 = (int32_t)nsplit; q.in[0].s2 = (int32_t)((int64_t)nsplit * pl.d1);
@@ -608,15 +697,25 @@ static int launch_fast_red(const RedPlan& pl, RedParams p, int vec, float* out, 
     p.dst = out; p.to_partial = 0;
   }
   dim3 grid((unsigned)gx, nsplit, (unsigned)O2);
+  // The single-launch scheme is NOT used for column sums: measured 52.8 vs 50.6 us on (8192,8192) --
+  // the fence + ticket in each of the 3.5 k short CTAs costs more than the 5 us second launch it saves
+  // (for full sums it replaces a 9 us single-CTA pass: 51.4 -> 47.5 us).  MDB_RED_COL_TICKETS=1 turns
+  // it on for measurements.
+  static const bool col_tickets = getenv("MDB_RED_COL_TICKETS") != nullptr;
+  if (col_tickets && vec == 4 && forms_ok && nsplit > 1 && gx * O2 <= kTickets) {
+    p.tickets = ticket_pool();
+    p.final_dst = out;
+  }
+  bool used_forms = false;
   if (vec == 4) {
-    if (forms_ok && launch_col_forms<OP, NIN, RED>(form, grid, p)) {}
+    if (forms_ok && (used_forms = launch_col_forms<OP, NIN, RED>(form, grid, p))) {}
     else if (NIN > 1 && late) red_col<OP, NIN, RED, 4, (NIN > 1)><<<grid, 256, 0, g_stream>>>(p);
     else red_col<OP, NIN, RED, 4><<<grid, 256, 0, g_stream>>>(p);
   } else {
     red_col<OP, NIN, RED, 1><<<grid, 256, 0, g_stream>>>(p);
   }
   MDB_CHECK_LAUNCH();
-  if (nsplit > 1) {
+  if (nsplit > 1 && !(used_forms && p.tickets)) {
     RedParams q = p;
     q.in[0].ptr = tmp.ptr; q.in[0].kind = K_F32; q.in[0].s0 = 1;
     q.in[0].s1 = (int32_t)I; q.in[0].s2 = (int32_t)((int64_t)nsplit * I);
