@@ -40,10 +40,10 @@ GEMM_ALGORITHMIC_BYTES_PER_LAUNCH = (
         (65536, 1024, 4096), (65536, 4096, 4096), (65536, 4096, 1024),
         (4096, 65536, 1024), (65536, 1024, 4096), (4096, 65536, 4096), (65536, 4096, 4096),
         (1024, 65536, 4096)]) / 8.0)
-# C2: DRAM bytes of the 13 launches of one iteration (ncu, profiles/r01_c2_launches_v2.csv)
-C2_TRAFFIC_BYTES_PER_ITER = 3.989e9
+# C2: DRAM bytes of the 13 launches of one iteration (ncu, profiles/r01_c2_launches_v3.csv)
+C2_TRAFFIC_BYTES_PER_ITER = 3.990e9
 C2_TRAFFIC_SRC = ("dram__bytes_read.sum + dram__bytes_write.sum over the 13 launches of one iteration, "
-                  "profiles/r01_c2_launches_v2.csv (below the algorithmic 4.295e9: part of each output is still "
+                  "profiles/r01_c2_launches_v3.csv (below the algorithmic 4.295e9: part of each output is still "
                   "in the 126 MB L2 when the next op reads it)")
 GLOBAL_BATCH = 65536
 DIMS = (1024, 4096, 4096, 1024)
