@@ -413,3 +413,76 @@ def test_exp_fp32_full_range_and_special_values(B):
         w = np.exp(sp)
     assert np.isnan(g[2]) and g[0] == np.inf and g[1] == 0.0 and g[3] == 1.0 and g[4] == 1.0
     assert ulp_diff(np.nan_to_num(g, nan=0.0, posinf=3e38), np.nan_to_num(w, nan=0.0, posinf=3e38)).max() <= 2
+
+
+# ---------------------------------------------------------------- form-specialised kernels
+# ew_rows (2-D broadcast binary ops, rows >= 2048 wide), red_row_f32 / red_col_f32 (fp32 sums with
+# compile-time operand forms, single-launch full sums).  Ragged extents (row length not a multiple
+# of the 1024-float4 CTA chunk, odd row counts), every operand form, outputs written into the
+# interior of a larger buffer with canary borders (an out-of-bounds store would corrupt them).
+WIDE_BIN = [((37, 2052), (37, 1)), ((37, 1), (1, 2052)), ((37, 2052), (2052,)), ((37, 2052), (1, 2052)),
+            ((3, 5, 4100), (5, 1)), ((3, 1, 4100), (1, 5, 1)), ((513, 8196), (513, 1))]
+
+
+@pytest.mark.parametrize("name", ["add", "subtract", "multiply", "true_divide"])
+@pytest.mark.parametrize("sa,sb", WIDE_BIN)
+def test_wide_broadcast_binary_exact(B, name, sa, sb):
+    a, b = f32(*sa), f32(*sb) + 3.0
+    for x, y in ((a, b), (b, a)):
+        check(getattr(B, name)(dev(B, x), dev(B, y)), getattr(np, name)(x, y))
+
+
+def test_wide_broadcast_inplace_into_view_keeps_canaries(B):
+    big = np.full((41, 2060), 7.0, np.float32)
+    d = B.asarray(big.copy())
+    view, ref = d[2:39, 4:2056], big[2:39, 4:2056]     # 37 x 2052 interior, 16-byte aligned rows
+    col, row = f32(37, 1), f32(1, 2052)
+    view += dev(B, col)
+    ref += col
+    view *= dev(B, row)
+    ref *= row
+    np.testing.assert_array_equal(d.numpy(), big)      # interior equal AND canary border untouched
+
+
+@pytest.mark.parametrize("shape", [(37, 2052), (513, 8196), (5, 3, 4100), (2049, 260)])
+def test_fused_gradient_sums_all_forms(B, shape):
+    """sum(t*c) / sum(t+k) over the last axis, the first axis and everything, with the second operand
+    a full array, a row vector, a column vector and a Python scalar (forms FV/FK/FS)."""
+    import ctypes as C
+
+    from minidiff_b200.backend import functions as F
+    from minidiff_b200.backend._lib import check as chk, lib
+
+    t = f32(*shape)
+    t64 = t.astype(np.float64)
+    last, first = shape[-1], shape[0]
+    others = {"full": f32(*shape), "rowvec": f32(*((1,) * (len(shape) - 1) + (last,))),
+              "colvec": f32(*(shape[:-1] + (1,))), "scalar": 2.5}
+    for tag, o in others.items():
+        o64 = np.asarray(o, dtype=np.float64)
+        for axes in ((len(shape) - 1,), (0,), tuple(range(len(shape)))):
+            want = (t64 * o64).sum(axis=axes, keepdims=True)
+            out = B.zeros(want.shape, dtype=np.float32)
+            ins = [B.asarray(t), B.asarray(o) if isinstance(o, np.ndarray) else o]
+            descs = (F.MdbArray * 2)()
+            for i, x in enumerate(ins):
+                if isinstance(x, B.DeviceArray):
+                    descs[i] = x.d
+                else:
+                    F._fill_imm(descs[i], x)
+            chk(lib.mdb_elementwise_reduce(F.OP["MUL"], C.byref(out.d), 2, descs, 0))
+            n_red = int(np.prod([shape[a] for a in axes]))
+            np.testing.assert_allclose(out.numpy(), want, rtol=1e-4, atol=2e-5 * np.sqrt(n_red), err_msg=f"{tag} {axes}")
+    # plain sums / means through the public functions (single-launch full sum included)
+    for axis in (None, 0, len(shape) - 1):
+        n_red = t.size if axis is None else shape[axis]
+        np.testing.assert_allclose(host(B.sum(dev(B, t), axis=axis)), t64.sum(axis=axis), rtol=1e-4,
+                                   atol=2e-5 * np.sqrt(n_red))
+        np.testing.assert_allclose(host(B.mean(dev(B, t), axis=axis)), t64.mean(axis=axis), rtol=1e-4, atol=1e-6)
+
+
+def test_full_sum_single_launch_is_repeatable_and_resets_its_tickets(B):
+    t = dev(B, f32(4096, 4100))
+    first = float(host(B.sum(t)))
+    for _ in range(5):                                   # a stale ticket would hang or change the result
+        assert float(host(B.sum(t))) == first
