@@ -575,6 +575,15 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
               const uint64_t da_lo = make_desc(a_lo + k * a_kstep, a_lbo, a_sbo, a_lt);
               const uint64_t db_hi = make_desc(b_hi + k * b_kstep, b_lbo, b_sbo, b_lt);
               const uint64_t db_lo = make_desc(b_lo + k * b_kstep, b_lbo, b_sbo, b_lt);
+              if (kTiming && (p.flags & 65536)) {
+                // diagnostic (wrong results): A operand from tensor memory -- what would the period be
+                // if the tensor core did not read the A tiles from shared memory?
+                const uint32_t ta = tmem_base + (acc ^ 1) * 256 + k * 8;
+                umma_tf32_pair_ts(tmem_d, ta, db_hi, idesc, 1);
+                umma_tf32_pair_ts(tmem_d, ta, db_lo, idesc, 1);
+                umma_tf32_pair_ts(tmem_d, ta + 32, db_hi, idesc, 1);
+                continue;
+              }
               if (kTiming && (p.flags & (128 | 256))) {
                 // diagnostic build only (results are wrong): 128 = alternate the two TMEM buffers
                 // between consecutive MMAs (no back-to-back dependency on one accumulator),
