@@ -173,6 +173,16 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
   return d;
 }
 
+// 16 consecutive 32-bit columns of this thread's TMEM lane  <-  16 registers
+#define MDB_TMEM_ST16(taddr, r)                                                                          \
+  asm volatile(                                                                                          \
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "                                                    \
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"                         \
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),        \
+        "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]),     \
+        "r"(r[15])                                                                                       \
+      : "memory")
+
 #define MDB_TMEM_LD32(taddr, r)                                                                          \
   asm volatile(                                                                                          \
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                          \

@@ -14,7 +14,7 @@ b = B.asarray(rng.standard_normal((n, n), dtype=np.float32))
 nc = 4 | 32 | 512 | 256
 # 512 = no conversion, 256 = hi*hi MMAs only, 128 = alternate accumulators, 4096 = L2-resident k range,
 # 16384 = .release.cluster remote arrives (all wrong-result switches exist in the diagnostic build only)
-for name, fl in (("pair43", 4 | 32), ("pair43", 4 | 32), ("pair52", 4 | 32 | 64), ("noconv43", 4 | 32 | 512), ("hihi43", 4 | 32 | 256),
+for name, fl in (("pair_ts", 4 | 32 | 131072), ("pair_ts", 4 | 32 | 131072), ("pair43", 4 | 32), ("pair43", 4 | 32), ("pair52", 4 | 32 | 64), ("noconv43", 4 | 32 | 512), ("hihi43", 4 | 32 | 256),
                  ("nc-hihi43", nc), ("release-arrive", 4 | 32 | 16384), ("A-from-TMEM", 4 | 32 | 65536),
                  ("A-from-TMEM-noconv", 4 | 32 | 65536 | 512)):
     check(lib.mdb_gemm_tune(fl))

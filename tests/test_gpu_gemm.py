@@ -127,3 +127,20 @@ def test_launch_is_tensor_core_for_large_shapes(B):
     check(lib.mdb_prof_enable(0))
     assert n.value == 1 and fl.value == 2.0 * 1024 ** 3
     assert fl.value / (ms.value * 1e-3) > 40e12, f"{fl.value / ms.value / 1e9:.1f} TFLOP/s: not the tensor-core path"
+
+
+@pytest.mark.parametrize("layout", ["NN", "NT", "TN", "TT"])
+def test_experimental_tmem_a_kernel_is_correct(B, layout):
+    """The A-operand-in-tensor-memory pair kernel (mdb_gemm_tune bit 17) is never selected by the
+    dispatcher (it is slower: single-buffered accumulator), but it must stay a correct reference."""
+    from minidiff_b200.backend._lib import check, lib
+
+    check(lib.mdb_gemm_config(2))
+    check(lib.mdb_gemm_tune(4 | 32 | 131072))
+    try:
+        for M, K, N in [(300, 260, 272), (1024, 1024, 768)]:
+            a, b, da, db = operands(B, M, K, N, layout, seed=M + N)
+            np.testing.assert_allclose(B.matmul(da, db).numpy(), a @ b, rtol=1e-4, atol=1e-5 * np.sqrt(K))
+    finally:
+        check(lib.mdb_gemm_tune(4))
+        check(lib.mdb_gemm_config(0))
