@@ -10,8 +10,13 @@ Headline line (one JSON object on stdout, rank 0):
   roofline       = the dominant kernel class of the step (GEMM), timed live with CUDA events on the
                    library's launch stream during the timed region.
   cpu_baseline   = the NumPy oracle port of the same step on this box's host cores (bounded sample).
-  fwd_bwd (N=1)  = the single-GPU graph benchmarks of BASELINE.json: config 2 (broadcast chain,
-                   GB/s vs HBM roofline) and config 3 (matmul fwd+bwd, TFLOP/s vs tensor roofline).
+  fwd_bwd (N=1)  = the single-GPU graph benchmarks of BASELINE.json: config 1 (README example, eager
+                   vs one CUDA-graph replay, microseconds), config 2 (broadcast chain, GB/s vs HBM
+                   roofline), config 3 (matmul fwd+bwd) and config 5 (Hessian-vector product), TFLOP/s
+                   vs the tensor roofline.
+  tensor roofline denominator = cuBLAS TF32 at 8192^3 measured in the same run (burst and sustained,
+                   the way MEASURED_PEAKS.json measures bf16); pipe_frac = 3 * frac because a 3xTF32
+                   GEMM issues three tensor-core MACs per fp32 product.
 
 `--impl reference` times the reference's CPU path (oracle port of the unmodified algorithm on
 NumPy/OpenBLAS with all host threads) on a bounded sample of the same workload.
