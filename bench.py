@@ -236,6 +236,20 @@ class Dev:
         self.check(self.lib.mdb_h2d(dst_tensor._data.ptr, pinned_view.ctypes.data, pinned_view.nbytes))
 
 
+def warm_until_stable(dev, fn, min_iters, max_iters=12):
+    """Untimed warm-up: at least `min_iters` calls, then until one whole call makes no cudaMalloc
+    (the caching allocator has every block size of this workload; a cudaMalloc inside a timed region
+    is a device-wide synchronisation worth milliseconds)."""
+    out = None
+    for i in range(max_iters):
+        before = dev.mem()["device_allocs"]
+        out = fn()
+        if i + 1 >= min_iters and dev.mem()["device_allocs"] == before:
+            break
+    dev.sync()
+    return out
+
+
 def dist_setup(world):
     if world == 1:
         return None
@@ -400,9 +414,7 @@ def bench_c2(dev, steps, warmup, peaks):
 
     a_np, c_np = W.c2_inputs()
     a, c = md.Tensor(a_np, allow_grad=True), md.Tensor(c_np, allow_grad=True)
-    for _ in range(warmup):
-        W.c2_step(a, c)
-    dev.sync()
+    warm_until_stable(dev, lambda: W.c2_step(a, c), warmup)
     time.sleep(0.3)          # let the power state settle after the GEMM-heavy headline loop
     # pass 1: whole-iteration device time, no per-launch profiler events on the stream (the event
     # pairs cost ~5 us per launch, 8 % of this 13-launch iteration)
@@ -451,9 +463,7 @@ def bench_c3(dev, steps, warmup, peaks, n=8192):
 
     A_np, B_np = W.c3_inputs(n)
     A, B = md.Tensor(A_np, allow_grad=True), md.Tensor(B_np, allow_grad=True)
-    for _ in range(warmup):
-        W.c3_step(A, B)
-    dev.sync()
+    warm_until_stable(dev, lambda: W.c3_step(A, B), warmup)
     e0, e1 = dev.event(), dev.event()
     dev.prof(True)
     dev.record(e0)
@@ -529,12 +539,11 @@ def bench_c5(dev, steps, warmup, peaks, batch=8192):
     vs = [md.Tensor(np.random.default_rng(50 + i).standard_normal(p.shape).astype(np.float32))
           for i, p in enumerate(params)]
     X, Y = md.Tensor(X_np), md.Tensor(Y_np)
-    for _ in range(warmup):
-        W.hvp(X, Y, params, vs)
-    dev.sync()
+    warm_until_stable(dev, lambda: W.hvp(X, Y, params, vs), warmup)
     e0, e1 = dev.event(), dev.event()
     dev.prof(True)
     l0 = dev.launches()
+    allocs0 = dev.mem()["device_allocs"]
     dev.record(e0)
     for _ in range(steps):
         hv = W.hvp(X, Y, params, vs)
@@ -549,6 +558,7 @@ def bench_c5(dev, steps, warmup, peaks, batch=8192):
                         "then backward of sum(grad*v)",
             "ms_per_iter": ms, "launches_per_iter": (dev.launches() - l0) / steps,
             "gemm_launches_per_iter": g_n / steps, "gemm_flops_per_iter": g_fl / steps,
+            "device_allocs_in_timed_region": dev.mem()["device_allocs"] - allocs0,
             "hv_norm": float(md.sum(hv[0] * hv[0]).item()) ** 0.5,
             "roofline": {"bound": "tensor", "achieved": tf, "peak": tf32_peak, "unit": "TFLOP/s",
                          "frac": tf / tf32_peak, "pipe_frac": 3.0 * tf / tf32_peak, "traffic": None,

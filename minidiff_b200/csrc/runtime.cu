@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <map>
+#include <set>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -35,17 +36,34 @@ int ensure_init() {
 }
 
 // ---- caching allocator ---------------------------------------------------------------------
-// Blocks are rounded to a size class and kept on per-class free lists when released.  Reuse is
-// safe without events because every consumer runs on the single compute stream (stream order ==
-// program order); the comm stream only touches buffers between mdb_comm_allreduce_* and
+// Small requests (< 1 MiB): exact 512-B size classes on per-class free lists, one cudaMalloc each.
+// Large requests (2 MiB granules): blocks live inside cudaMalloc'ed SEGMENTS and are split and
+// coalesced -- best fit over all cached blocks; a block more than 1.5x the request is split and the
+// remainder stays cached; freed neighbours merge.  Workloads that change shape (the bench runs a
+// 65536-row MLP, then 8192^3 GEMMs, then an 8192-row HVP) therefore reuse the same segments instead
+// of paying a device-wide cudaMalloc synchronisation per new size (the first version kept whole
+// blocks per size class: 66 cudaMallocs and +3 GB of cache when the HVP followed the MLP).
+// Reuse is safe without events because every consumer runs on the single compute stream (stream
+// order == program order); the comm stream only touches buffers between mdb_comm_allreduce_* and
 // mdb_comm_wait, during which the frontend keeps them alive.
+//
 // CUDA-graph capture (mdb_graph_*): a captured graph replays the SAME addresses, so every block that
 // is handed out while a capture is open is tagged with that graph's private pool: when released --
 // during the capture or any time later -- it returns to the pool, never to the general cache, until
 // the graph is destroyed.  Temporaries are therefore recycled inside one capture exactly as they
 // are in eager mode, and nothing outside the graph can be given memory the graph writes on replay.
+// Pool blocks are never split or merged.
+struct GraphPool;
+struct Block {
+  char* ptr;
+  size_t size;
+  bool is_free;
+  bool small;                 // stand-alone cudaMalloc of a small size class (never split / merged)
+  Block *prev, *next;         // address-ordered neighbours inside the same segment
+  GraphPool* owner;           // non-null: belongs to a captured graph
+};
 struct GraphPool {
-  std::map<size_t, std::vector<void*>> free_lists;
+  std::map<size_t, std::vector<Block*>> free_lists;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   uint64_t launches = 0;     // kernel launches recorded while capturing (added per replay)
@@ -53,102 +71,166 @@ struct GraphPool {
 };
 
 struct Allocator {
-  std::map<size_t, std::vector<void*>> free_lists;
-  std::unordered_map<void*, size_t> live;
-  std::unordered_map<void*, GraphPool*> owner;   // blocks (live or pooled) that belong to a graph
+  static constexpr size_t kSmall = size_t(1) << 20, kGranule = size_t(2) << 20;
+  std::map<size_t, std::vector<Block*>> small_free;          // size class -> blocks
+  std::set<std::pair<size_t, Block*>> large_free;            // (size, block): best fit = lower_bound
+  std::unordered_map<void*, Block*> live;
   GraphPool* capturing = nullptr;
   size_t in_use = 0, cached = 0, peak = 0;
   uint64_t n_device_allocs = 0;
 
   static size_t round(size_t b) {
     if (b == 0) b = 1;
-    if (b <= (1u << 20)) return (b + 511) & ~size_t(511);           // 512 B classes below 1 MiB
-    return (b + ((2u << 20) - 1)) & ~size_t((2u << 20) - 1);        // 2 MiB classes above
+    if (b <= kSmall) return (b + 511) & ~size_t(511);
+    return (b + kGranule - 1) & ~(kGranule - 1);
   }
-  static bool take(std::map<size_t, std::vector<void*>>& lists, size_t& r, void** out) {
-    auto it = lists.lower_bound(r);
-    while (it != lists.end() && it->second.empty()) ++it;
-    if (it != lists.end() && (it->first == r || (r >= (8u << 20) && it->first <= r + r / 2))) {
-      r = it->first;
-      *out = it->second.back();
-      it->second.pop_back();
-      return true;
-    }
-    return false;
+  void account_out(Block* b, void** out) {
+    b->is_free = false;
+    live[b->ptr] = b;
+    in_use += b->size;
+    if (in_use > peak) peak = in_use;
+    if (capturing) { b->owner = capturing; capturing->bytes += b->size; }
+    *out = b->ptr;
   }
-  int alloc(size_t bytes, void** out) {
-    size_t r = round(bytes);
-    if (capturing && take(capturing->free_lists, r, out)) {     // recycled inside this graph
-      live[*out] = r;
-      in_use += r;
-      if (in_use > peak) peak = in_use;
-      return 0;
-    }
-    // exact class first, then the smallest cached block within 1.5x (large blocks only): a
-    // cudaMalloc is a device-wide synchronisation and costs milliseconds at GB sizes
-    auto it = free_lists.lower_bound(r);
-    while (it != free_lists.end() && it->second.empty()) ++it;
-    if (it != free_lists.end() && (it->first == r || (r >= (8u << 20) && it->first <= r + r / 2))) {
-      r = it->first;
-      *out = it->second.back();
-      it->second.pop_back();
-      cached -= r;
-    } else {
-      static const bool trace = getenv("MDB_ALLOC_TRACE") != nullptr;
-      if (trace) {
-        size_t nfree = 0;
-        for (auto& kv : free_lists) nfree += kv.second.size();
-        fprintf(stderr, "[mdb alloc miss] %.1f MB (request %.1f MB), cached blocks %zu / %.1f MB\n", r / 1e6,
-                bytes / 1e6, nfree, cached / 1e6);
-      }
-      cudaError_t e = cudaMalloc(out, r);
+  int device_alloc(size_t r, bool small, Block** out) {
+    static const bool trace = getenv("MDB_ALLOC_TRACE") != nullptr;
+    if (trace) fprintf(stderr, "[mdb alloc miss] %.1f MB, cached %.1f MB\n", r / 1e6, cached / 1e6);
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, r);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      release_cached();
+      e = cudaMalloc(&p, r);
       if (e != cudaSuccess) {
         cudaGetLastError();
-        release_cached();
-        e = cudaMalloc(out, r);
-        if (e != cudaSuccess) {
-          cudaGetLastError();
-          return set_error(MDB_ENOMEM, "out of device memory allocating %zu bytes (%s)", r,
-                           cudaGetErrorString(e));
-        }
+        return set_error(MDB_ENOMEM, "out of device memory allocating %zu bytes (%s)", r, cudaGetErrorString(e));
       }
-      ++n_device_allocs;
     }
-    live[*out] = r;
-    in_use += r;
-    if (in_use > peak) peak = in_use;
-    if (capturing) { owner[*out] = capturing; capturing->bytes += r; }
+    ++n_device_allocs;
+    *out = new Block{(char*)p, r, false, small, nullptr, nullptr, nullptr};
     return 0;
+  }
+  int alloc(size_t bytes, void** out) {
+    const size_t r = round(bytes);
+    const bool small = r <= kSmall;
+    if (capturing) {                                          // recycled inside this graph first
+      auto it = capturing->free_lists.lower_bound(r);
+      while (it != capturing->free_lists.end() && it->second.empty()) ++it;
+      if (it != capturing->free_lists.end() && (it->first == r || (!small && it->first <= r + r / 2))) {
+        Block* b = it->second.back();
+        it->second.pop_back();
+        b->is_free = false;
+        live[b->ptr] = b;
+        in_use += b->size;
+        if (in_use > peak) peak = in_use;
+        *out = b->ptr;
+        return 0;
+      }
+    }
+    Block* b = nullptr;
+    if (small) {
+      auto it = small_free.find(r);
+      if (it != small_free.end() && !it->second.empty()) {
+        b = it->second.back();
+        it->second.pop_back();
+        cached -= b->size;
+      } else {
+        MDB_TRY(device_alloc(r, true, &b));
+      }
+    } else {
+      auto it = large_free.lower_bound({r, nullptr});
+      if (it != large_free.end()) {
+        b = it->second;
+        large_free.erase(it);
+        cached -= b->size;
+        if (b->size > r + r / 2 && b->size - r >= kGranule) {   // split: the tail stays cached
+          Block* tail = new Block{b->ptr + r, b->size - r, true, false, b, b->next, nullptr};
+          if (b->next) b->next->prev = tail;
+          b->next = tail;
+          b->size = r;
+          large_free.insert({tail->size, tail});
+          cached += tail->size;
+        }
+      } else {
+        MDB_TRY(device_alloc(r, false, &b));
+      }
+    }
+    account_out(b, out);
+    return 0;
+  }
+  void insert_free_large(Block* b) {       // merge with free, unowned neighbours of the same segment
+    while (b->next && b->next->is_free && !b->next->owner) {
+      Block* n = b->next;
+      large_free.erase({n->size, n});
+      cached -= n->size;
+      b->size += n->size;
+      b->next = n->next;
+      if (n->next) n->next->prev = b;
+      delete n;
+    }
+    while (b->prev && b->prev->is_free && !b->prev->owner) {
+      Block* q = b->prev;
+      large_free.erase({q->size, q});
+      cached -= q->size;
+      q->size += b->size;
+      q->next = b->next;
+      if (b->next) b->next->prev = q;
+      delete b;
+      b = q;
+    }
+    b->is_free = true;
+    large_free.insert({b->size, b});
+    cached += b->size;
   }
   int free(void* p) {
     auto it = live.find(p);
     if (it == live.end()) return set_error(MDB_EINVAL, "mdb_free: unknown pointer %p", p);
-    size_t r = it->second;
+    Block* b = it->second;
     live.erase(it);
-    in_use -= r;
-    auto ow = owner.find(p);
-    if (ow != owner.end()) {                 // graph memory goes back to its graph only
-      ow->second->free_lists[r].push_back(p);
+    in_use -= b->size;
+    if (b->owner) {                          // graph memory goes back to its graph only
+      b->is_free = true;
+      b->owner->free_lists[b->size].push_back(b);
       return 0;
     }
-    cached += r;
-    free_lists[r].push_back(p);
+    if (b->small) {
+      b->is_free = true;
+      small_free[b->size].push_back(b);
+      cached += b->size;
+    } else {
+      insert_free_large(b);
+    }
     return 0;
   }
   // the graph is gone: its pooled blocks join the general cache, its live blocks become ordinary
   void dissolve(GraphPool* g) {
     for (auto& kv : g->free_lists)
-      for (void* p : kv.second) { owner.erase(p); free_lists[kv.first].push_back(p); cached += kv.first; }
+      for (Block* b : kv.second) {
+        b->owner = nullptr;
+        if (b->small) { small_free[b->size].push_back(b); cached += b->size; }
+        else { b->is_free = false; insert_free_large(b); }
+      }
     g->free_lists.clear();
-    for (auto it = owner.begin(); it != owner.end();)
-      if (it->second == g) it = owner.erase(it); else ++it;
+    for (auto& kv : live)
+      if (kv.second->owner == g) kv.second->owner = nullptr;
   }
   void release_cached() {
     if (g_stream) cudaStreamSynchronize(g_stream);
-    for (auto& kv : free_lists)
-      for (void* p : kv.second) cudaFree(p);
-    free_lists.clear();
-    cached = 0;
+    for (auto& kv : small_free)
+      for (Block* b : kv.second) { cudaFree(b->ptr); cached -= b->size; delete b; }
+    small_free.clear();
+    // only whole segments can go back to the driver: a free block with no neighbours left
+    for (auto it = large_free.begin(); it != large_free.end();) {
+      Block* b = it->second;
+      if (!b->prev && !b->next) {
+        cudaFree(b->ptr);
+        cached -= b->size;
+        delete b;
+        it = large_free.erase(it);
+      } else {
+        ++it;
+      }
+    }
   }
 };
 static Allocator g_alloc;

@@ -486,3 +486,57 @@ def test_full_sum_single_launch_is_repeatable_and_resets_its_tickets(B):
     first = float(host(B.sum(t)))
     for _ in range(5):                                   # a stale ticket would hang or change the result
         assert float(host(B.sum(t))) == first
+
+
+def test_allocator_split_coalesce_stress(B):
+    """Large blocks are split from and merged back into cached segments: random alloc / free traffic
+    must never hand out overlapping ranges, must return in_use to its starting value, and a repeating
+    mix of sizes must stop calling cudaMalloc once the segments exist."""
+    import ctypes as C
+
+    from minidiff_b200.backend._lib import check, lib
+
+    def stats():
+        v = [C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_uint64()]
+        lib.mdb_mem_stats(*[C.byref(x) for x in v])
+        return [x.value for x in v]
+
+    rng = np.random.default_rng(0)
+    in_use0 = stats()[0]
+    live = {}
+    MiB = 1 << 20
+
+    def alloc(nbytes):
+        p = C.c_void_p()
+        check(lib.mdb_alloc(nbytes, C.byref(p)))
+        lo, hi = p.value, p.value + nbytes
+        for q, n in live.items():
+            assert hi <= q or lo >= q + n, "overlapping allocations"
+        live[p.value] = nbytes
+
+    def free_one():
+        q = list(live)[int(rng.integers(len(live)))]
+        check(lib.mdb_free(q))
+        del live[q]
+
+    sizes = [3 * MiB, 16 * MiB, 33 * MiB, 64 * MiB, 130 * MiB, 256 * MiB, 700, 40000]
+    for it in range(600):
+        if live and (len(live) > 24 or rng.random() < 0.45):
+            free_one()
+        else:
+            alloc(int(sizes[int(rng.integers(len(sizes)))]))
+    while live:
+        free_one()
+    assert stats()[0] == in_use0
+    # steady state: the same traffic again is served from the cache
+    n0 = stats()[3]
+    rng = np.random.default_rng(0)
+    for it in range(600):
+        if live and (len(live) > 24 or rng.random() < 0.45):
+            free_one()
+        else:
+            alloc(int(sizes[int(rng.integers(len(sizes)))]))
+    while live:
+        free_one()
+    assert stats()[3] - n0 <= 2, f"{stats()[3] - n0} cudaMallocs in the repeated pass"
+    B.synchronize()
