@@ -568,9 +568,25 @@ def bench_c5(dev, steps, warmup, peaks, batch=8192):
 # ------------------------------------------------------------------------------------------------
 # CPU arms (oracle port == the reference's algorithm on NumPy/OpenBLAS)
 # ------------------------------------------------------------------------------------------------
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1, which would pin OpenBLAS (the reference's matmul) to one
+    thread; the CPU arms are meant to use every host core.  Returns the thread count in effect."""
+    n = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+
+        threadpool_limits(limits=n)
+        got = [i.get("num_threads") for i in threadpool_info() if i.get("user_api") == "blas"]
+        return max(got) if got else n
+    except Exception:
+        return int(os.environ.get("OMP_NUM_THREADS", n))
+
+
 def cpu_mlp_samples_per_s(sample_batch, reps):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import np_minidiff as orc
+
+    use_all_host_threads()
 
     X, Y = orc.mlp_data(sample_batch, DIMS[0], DIMS[-1])
     ps = orc.mlp_params(DIMS)
@@ -587,7 +603,7 @@ def cpu_mlp_samples_per_s(sample_batch, reps):
 def reference_arm(args, rank):
     if rank != 0:
         return
-    cores = os.cpu_count()
+    cores = use_all_host_threads()
     sample = 8192
     times = []
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
