@@ -144,3 +144,25 @@ def test_experimental_tmem_a_kernel_is_correct(B, layout):
     finally:
         check(lib.mdb_gemm_tune(4))
         check(lib.mdb_gemm_config(0))
+
+
+def test_random_shapes_fuzz(B):
+    """Seeded fuzz over the dispatcher (pair / single / CUDA-core kernels chosen automatically):
+    random extents (ragged against every tile size), random operand layouts, plain and accumulate."""
+    from minidiff_b200.backend import functions as F
+
+    rng = np.random.default_rng(2026)
+    for case in range(36):
+        M, N = int(rng.integers(33, 1400)), int(rng.integers(33, 1400))
+        K = int(rng.integers(32, 2600))
+        layout = ["NN", "NT", "TN", "TT"][int(rng.integers(4))]
+        a, b, da, db = operands(B, M, K, N, layout, seed=1000 + case)
+        truth = a.astype(np.float64) @ b.astype(np.float64)
+        tol = dict(rtol=1e-4, atol=1.5e-5 * np.sqrt(K))
+        if case % 3 == 2:
+            c0 = rng.standard_normal((M, N)).astype(np.float32)
+            dc = B.asarray(c0.copy())
+            F._gemm(da, db, out=dc, accumulate=True)
+            np.testing.assert_allclose(dc.numpy(), c0 + truth, err_msg=f"{M}x{K}x{N} {layout} acc", **tol)
+        else:
+            np.testing.assert_allclose(B.matmul(da, db).numpy(), truth, err_msg=f"{M}x{K}x{N} {layout}", **tol)
