@@ -296,6 +296,7 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool vec_ok = (p.ldc % 4 == 0) && (((uintptr_t)p.C & 15) == 0);
+    const bool vec8_ok = (p.ldc % 8 == 0) && (((uintptr_t)p.C & 31) == 0) && !(p.flags & 1048576);   // 1048576: A/B, 128-bit stores
     const int num_chunks = (num_k + kChunk - 1) / kChunk;
     long long w_full = 0, t_all = MDB_T0();
     for (int t = first_tile; t < num_tiles; t += tile_step) {
@@ -325,12 +326,24 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
         if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (row < p.M) {
+      if (row < p.M && !(kTiming && (p.flags & 524288))) {   // 524288: diagnostic, skip the C store
         float* crow = p.C + (int64_t)row * p.ldc;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int col0 = n0 + c * 32;
-          if (vec_ok && col0 + 32 <= p.N) {
+          if (vec8_ok && !p.accumulate && col0 + 32 <= p.N) {
+            // 256-bit stores (sm_100): every instruction writes one whole 32-B sector of this thread's
+            // row.  With 128-bit stores each sector took two half-writes and the tile store
+            // (128 KB per CTA, all CTAs at once) outlasted the two chunks of TMEM lookahead: ~50 us
+            // of exposed store time per 128 MB of output.
+#pragma unroll
+            for (int j = 0; j < 32; j += 8)
+              asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(crow + col0 + j),
+                           "f"(sum[c * 32 + j]), "f"(sum[c * 32 + j + 1]), "f"(sum[c * 32 + j + 2]),
+                           "f"(sum[c * 32 + j + 3]), "f"(sum[c * 32 + j + 4]), "f"(sum[c * 32 + j + 5]),
+                           "f"(sum[c * 32 + j + 6]), "f"(sum[c * 32 + j + 7])
+                           : "memory");
+          } else if (vec_ok && col0 + 32 <= p.N) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               float4 v = make_float4(sum[c * 32 + j], sum[c * 32 + j + 1], sum[c * 32 + j + 2], sum[c * 32 + j + 3]);
