@@ -186,6 +186,10 @@ int mdb_comm_init(int rank, int world, const void* id128, const char* nccl_lib_p
 int mdb_comm_allreduce_f32(void* ptr, size_t count, int average);        /* on the comm stream,
                                                                             ordered after compute */
 int mdb_comm_wait(void);                          /* compute stream waits for the comm stream    */
+/* per-exchange completion: every mdb_comm_allreduce_f32 gets the next sequence number; the compute
+ * stream can wait for ONE of them (update that parameter while later gradients are still in flight) */
+uint64_t mdb_comm_last_seq(void);
+int mdb_comm_wait_seq(uint64_t seq);
 int mdb_comm_destroy(void);
 
 #ifdef __cplusplus

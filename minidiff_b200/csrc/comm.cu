@@ -28,6 +28,11 @@ static fn_GetErrorString p_GetErrorString;
 static ncclComm_t g_comm = nullptr;
 static cudaStream_t g_comm_stream = nullptr;
 static cudaEvent_t g_ev_compute = nullptr, g_ev_comm = nullptr;
+// one completion event per all-reduce (ring): the optimiser can wait for ONE parameter's exchange and
+// update it while the exchange of later gradients is still in flight
+constexpr int kSeqRing = 64;
+static cudaEvent_t g_ev_seq[kSeqRing] = {};
+static uint64_t g_seq = 0;
 static int g_world = 1;
 
 static int load_nccl(const char* path) {
@@ -78,6 +83,8 @@ int mdb_comm_init(int rank, int world, const void* id128, const char* nccl_lib_p
   MDB_CUDA(cudaStreamCreateWithFlags(&g_comm_stream, cudaStreamNonBlocking));
   MDB_CUDA(cudaEventCreateWithFlags(&g_ev_compute, cudaEventDisableTiming));
   MDB_CUDA(cudaEventCreateWithFlags(&g_ev_comm, cudaEventDisableTiming));
+  for (int i = 0; i < kSeqRing; ++i) MDB_CUDA(cudaEventCreateWithFlags(&g_ev_seq[i], cudaEventDisableTiming));
+  g_seq = 0;
   MDB_NCCL(p_CommInitRank(&g_comm, world, id, rank));
   g_world = world;
   return 0;
@@ -92,6 +99,19 @@ int mdb_comm_allreduce_f32(void* ptr, size_t count, int average) {
   MDB_NCCL(p_AllReduce(ptr, ptr, count, ncclFloat32, average ? ncclAvg : ncclSum, g_comm,
                        g_comm_stream));
   MDB_CUDA(cudaEventRecord(g_ev_comm, g_comm_stream));
+  ++g_seq;
+  MDB_CUDA(cudaEventRecord(g_ev_seq[g_seq % kSeqRing], g_comm_stream));
+  return 0;
+}
+
+uint64_t mdb_comm_last_seq(void) { return g_seq; }
+
+int mdb_comm_wait_seq(uint64_t seq) {
+  if (g_comm == nullptr || seq == 0) return 0;
+  // an entry that has left the ring was followed by >= 64 later all-reduces on the same in-order
+  // stream: waiting for the newest one covers it
+  const uint64_t s = (seq + kSeqRing <= g_seq) ? g_seq : seq;
+  MDB_CUDA(cudaStreamWaitEvent(g_stream, g_ev_seq[s % kSeqRing], 0));
   return 0;
 }
 
@@ -108,6 +128,7 @@ int mdb_comm_destroy(void) {
     cudaStreamDestroy(g_comm_stream);
     cudaEventDestroy(g_ev_compute);
     cudaEventDestroy(g_ev_comm);
+    for (int i = 0; i < kSeqRing; ++i) if (g_ev_seq[i]) { cudaEventDestroy(g_ev_seq[i]); g_ev_seq[i] = nullptr; }
     g_comm = nullptr;
   }
   return 0;

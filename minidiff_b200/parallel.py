@@ -44,6 +44,8 @@ class DataParallel:
         self.params = list(params)
         self.overlap = overlap
         self._pending = False
+        self._seq = {}
+        self._flushed = False
         if self.world == 1:
             return
         if not dist.is_initialized():
@@ -83,18 +85,39 @@ class DataParallel:
             p.grad = md.Tensor(F.astype(g, np.float32))
             g = p.grad._data
         check(lib.mdb_comm_allreduce_f32(g.ptr, g.size, 1))
+        self._seq[id(p)] = int(lib.mdb_comm_last_seq())
         self._pending = True
+
+    def flush(self):
+        """Issue the exchanges that the backward hooks did not (overlap=False); no waiting."""
+        if self.world > 1 and not self.overlap and not self._flushed:
+            for p in self.params:
+                self._allreduce(p)
+            self._flushed = True
+
+    def wait(self, p):
+        """Order the compute stream after the exchange of THIS parameter's gradient only, so the
+        optimiser can update early layers' parameters while later exchanges are still in flight."""
+        if self.world == 1:
+            return
+        seq = self._seq.pop(id(p), 0)
+        if seq:
+            check(lib.mdb_comm_wait_seq(seq))
+
+    def update_order(self):
+        """Parameters in the order their gradients finish in the backward sweep (last layer first)."""
+        return list(reversed(self.params))
 
     def finish(self):
         """All gradients averaged and visible to the compute stream after this returns (async)."""
         if self.world == 1:
             return
-        if not self.overlap:
-            for p in self.params:
-                self._allreduce(p)
+        self.flush()
         if self._pending:
             check(lib.mdb_comm_wait())
             self._pending = False
+        self._seq.clear()
+        self._flushed = False
 
     def close(self):
         if self.world > 1:

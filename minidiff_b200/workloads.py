@@ -79,11 +79,19 @@ def mlp_train_step(X, Y, params, lr=0.01, dp=None):
     """Full training step: forward, mean-MSE, backward, (DP: all-reduce grads), SGD under no_grad."""
     loss = md.mean((mlp_forward(X, params) - Y) ** 2)
     loss.backward()
-    if dp is not None:
-        dp.finish()
+    if dp is None:
+        with md.no_grad():
+            for p in params:
+                p -= lr * p.grad
+        return loss
+    # data parallel: update each parameter as soon as ITS gradient has been averaged, last layer
+    # first (the order the backward sweep finished them), while later exchanges are still in flight
+    dp.flush()
     with md.no_grad():
-        for p in params:
+        for p in dp.update_order():
+            dp.wait(p)
             p -= lr * p.grad
+    dp.finish()
     return loss
 
 
