@@ -57,8 +57,13 @@ struct PairParams {
 #define MDB_T0() (kTiming ? clock64() : 0ll)
 #define MDB_TACC(var, t0) do { if (kTiming) var += clock64() - (t0); } while (0)
 
-template <int kHi, int kLo, bool kTiming>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
+// kMc = 1: cluster of 2 (one pair).  kMc = 2: cluster of 4 = two pairs working on horizontally
+// adjacent tiles (same A rows): every A tile is fetched from L2 ONCE and TMA-multicast into both pairs
+// (each of the two CTAs that need it loads half of it for both), which cuts the L2 -> SM traffic by
+// a quarter.  A slot may only be refilled when BOTH pairs are done with it: hi_empty counts one
+// commit per pair, multicast to all four CTAs.
+template <int kHi, int kLo, bool kTiming, int kMc = 1>
+__global__ void __cluster_dims__(2 * kMc, 1, 1) __launch_bounds__(kPairThreads, 1)
 gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                         const PairParams p) {
   using S = Smem<PBN, kHi, kLo>;
@@ -74,7 +79,10 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t crank = cluster_ctarank();            // rank in the cluster (0..2*kMc-1)
+  const uint32_t rank = crank & 1;                      // rank inside the CTA pair
+  const uint32_t pair = crank >> 1;                     // which pair of the cluster (kMc = 2)
+  const uint32_t leader = crank & ~1u;                  // cluster rank of this pair's leader CTA
   const int first_tile = (int)cluster_id_x(), tile_step = (int)num_clusters_x();
   constexpr uint32_t kTmemCols = 512;            // two 256-column accumulator stages
   const int num_tiles = p.tiles_m * p.tiles_n;
@@ -87,7 +95,7 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kHi; ++s) { mbar_init(&hi_full[s], 1); mbar_init(&hi_empty[s], 1); }
+    for (int s = 0; s < kHi; ++s) { mbar_init(&hi_full[s], 1); mbar_init(&hi_empty[s], kMc); }
     for (int s = 0; s < kLo; ++s) { mbar_init(&lo_full[s], 2 * kPairConvWarps); mbar_init(&lo_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 2 * kPairEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -115,7 +123,7 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
       for (int t = first_tile; t < num_tiles; t += tile_step) {
         int m_blk, n_blk;
         tile_coords(tp, t, m_blk, n_blk);
-        const int m0 = m_blk * 256 + (int)rank * BM, n0 = n_blk * 256 + (int)rank * PBN;
+        const int m0 = m_blk * 256 + (int)rank * BM, n0 = (n_blk * kMc + (int)pair) * 256 + (int)rank * PBN;
         for (int kb = 0; kb < num_k; ++kb) {
           const int k0 = (kTiming && (p.flags & 4096)) ? (kb & 7) * BK : kb * BK;   // 4096: diagnostic, L2-resident k range
           const long long tw = MDB_T0();
@@ -125,10 +133,19 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
           uint64_t* hbar = &hi_full[hi.slot];
           mbar_expect_tx(hbar, S::SLOT_BYTES);
           if (!p.a_mn_major) {
-            tma_load_2d(a_hi, &map_a, hbar, k0, m0);
+            if constexpr (kMc == 1) {
+              tma_load_2d(a_hi, &map_a, hbar, k0, m0);
+            } else {               // this CTA fetches rows [64 pair, +64) of the tile for both pairs (box = 32 x 64)
+              tma_load_2d_mc(a_hi + pair * (64 * 128), &map_a, hbar, k0, m0 + 64 * (int)pair,
+                             (uint16_t)((1u << rank) | (1u << (rank + 2))));
+            }
           } else {
 #pragma unroll
-            for (int c = 0; c < BM / 32; ++c) tma_load_2d(a_hi + c * 4096, &map_a, hbar, m0 + 32 * c, k0);
+            for (int c = 0; c < BM / 32; ++c) {
+              if constexpr (kMc == 1) tma_load_2d(a_hi + c * 4096, &map_a, hbar, m0 + 32 * c, k0);
+              else if ((c >> 1) == (int)pair)     // two of the four 32-column boxes each, for both pairs
+                tma_load_2d_mc(a_hi + c * 4096, &map_a, hbar, m0 + 32 * c, k0, (uint16_t)((1u << rank) | (1u << (rank + 2))));
+            }
           }
           if (!p.b_mn_major) {
             tma_load_2d(b_hi, &map_b, hbar, k0, n0);
@@ -145,6 +162,7 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     // ===================================== MMA issuer (leader CTA only) ======================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (rank == 0) {
+      const uint16_t pair_mask = (uint16_t)(3u << (2 * pair)), all_mask = (uint16_t)((1u << (2 * kMc)) - 1);
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn_major << 15) |
                              ((uint32_t)p.b_mn_major << 16) | ((uint32_t)((2 * PBN) >> 3) << 17) |
                              ((uint32_t)(256 >> 4) << 24);
@@ -205,9 +223,9 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
               umma_tf32_pair(tmem_d, da_hi, db_lo, idesc, 1);
               umma_tf32_pair(tmem_d, da_hi, db_hi, idesc, 1);
             }
-            umma_commit_pair(&lo_empty[lo.slot]);
-            umma_commit_pair(&hi_empty[hi.slot]);
-            if (chunk_end) umma_commit_pair(&tmem_full[acc]);
+            umma_commit_pair(&lo_empty[lo.slot], pair_mask);
+            umma_commit_pair(&hi_empty[hi.slot], all_mask);       // kMc = 2: both pairs must release an A slot
+            if (chunk_end) umma_commit_pair(&tmem_full[acc], pair_mask);
           }
           __syncwarp();
           hi.advance(kHi);
@@ -276,8 +294,8 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> visible to UMMA
         __syncwarp();
         if (lane == 0) {                                               // tell the leader's MMA warp
-          if (kTiming && (p.flags & 16384)) mbar_arrive_cluster_release(&lo_full[lo.slot], 0);   // diagnostic: 28 % slower
-          else mbar_arrive_cluster(&lo_full[lo.slot], 0);
+          if (kTiming && (p.flags & 16384)) mbar_arrive_cluster_release(&lo_full[lo.slot], leader);   // diagnostic: 28 % slower
+          else mbar_arrive_cluster(&lo_full[lo.slot], leader);
         }
         MDB_TACC(t_sig, td);
         hi.advance(kHi);
@@ -303,7 +321,7 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
       int m_blk, n_blk;
       tile_coords(tp, t, m_blk, n_blk);
       const int row = m_blk * 256 + (int)rank * BM + q * 32 + lane;
-      const int n0 = n_blk * 256 + eh * 128;
+      const int n0 = (n_blk * kMc + (int)pair) * 256 + eh * 128;
       float sum[128];
 #pragma unroll
       for (int j = 0; j < 128; ++j) sum[j] = 0.f;
@@ -323,7 +341,7 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
         }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+        if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], leader);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       if (row < p.M && !(kTiming && (p.flags & 524288))) {   // 524288: diagnostic, skip the C store

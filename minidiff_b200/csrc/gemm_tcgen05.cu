@@ -510,43 +510,44 @@ typedef void (*PairKernel)(const CUtensorMap, const CUtensorMap, const tc::PairP
 
 // shared launcher of the CTA-pair kernels; `state` caches the occupancy query per instantiation
 static int launch_pair_impl(PairKernel kern, PairKernel tkern, int smem_total, int* state, const char* tag,
-                            const CUtensorMap& map_a, const CUtensorMap& map_b, const tc::PairParams& p) {
+                            const CUtensorMap& map_a, const CUtensorMap& map_b, const tc::PairParams& p,
+                            int cluster_ctas = 2) {
   int& max_clusters = *state;
   if (!max_clusters) {
     MDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(g_sm_count, 1, 1);
+    cfg.gridDim = dim3(g_sm_count / cluster_ctas * cluster_ctas, 1, 1);
     cfg.blockDim = dim3(tc::kPairThreads, 1, 1);
     cfg.dynamicSmemBytes = smem_total;
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    attr.val.clusterDim.x = cluster_ctas; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr; cfg.numAttrs = 1;
     int n = 0;
     if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
       cudaGetLastError();
-      n = g_sm_count / 2;
+      n = g_sm_count / cluster_ctas;
     }
-    max_clusters = std::min(n, g_sm_count / 2);
+    max_clusters = std::min(n, g_sm_count / cluster_ctas);
   }
   const int tiles = p.tiles_m * p.tiles_n;
   const int clusters = std::min(tiles, max_clusters);
   static const bool timing = getenv("MDB_GEMM_TIMING") != nullptr;
   if (!timing) {
-    kern<<<2 * clusters, tc::kPairThreads, smem_total, g_stream>>>(map_a, map_b, p);
+    kern<<<cluster_ctas * clusters, tc::kPairThreads, smem_total, g_stream>>>(map_a, map_b, p);
     MDB_CHECK_LAUNCH();
     return 0;
   }
   // diagnostic mode: per-role stall cycles, averaged over leader / follower CTAs, printed to stderr
   static unsigned long long* dbuf = nullptr;
   if (!dbuf) MDB_CUDA(cudaMalloc(&dbuf, 16 * 8 * 2 * 148));
-  MDB_CUDA(cudaMemsetAsync(dbuf, 0, 16 * 8 * 2 * clusters, g_stream));
+  MDB_CUDA(cudaMemsetAsync(dbuf, 0, 16 * 8 * cluster_ctas * clusters, g_stream));
   tc::PairParams q = p;
   q.timing = dbuf;
   MDB_CUDA(cudaFuncSetAttribute(tkern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total));
-  tkern<<<2 * clusters, tc::kPairThreads, smem_total, g_stream>>>(map_a, map_b, q);
+  tkern<<<cluster_ctas * clusters, tc::kPairThreads, smem_total, g_stream>>>(map_a, map_b, q);
   MDB_CHECK_LAUNCH();
-  std::vector<unsigned long long> h(16 * 2 * clusters);
+  std::vector<unsigned long long> h(16 * cluster_ctas * clusters);
   MDB_CUDA(cudaMemcpyAsync(h.data(), dbuf, h.size() * 8, cudaMemcpyDeviceToHost, g_stream));
   MDB_CUDA(cudaStreamSynchronize(g_stream));
   static const char* names[13] = {"prod.wait_hi_empty", "prod.total", "mma.wait_lo_full", "mma.wait_tmem_empty", "mma.total",
@@ -558,8 +559,9 @@ static int launch_pair_impl(PairKernel kern, PairKernel tkern, int smem_total, i
   for (int i = 0; i < 13; ++i) {
     if (i == 5) continue;
     double s[2] = {0, 0};
-    for (int c = 0; c < 2 * clusters; ++c) s[c & 1] += (double)h[c * 16 + i];
-    fprintf(stderr, "  %-22s %9.1f | %9.1f\n", names[i], s[0] / clusters / kblocks, s[1] / clusters / kblocks);
+    for (int c = 0; c < cluster_ctas * clusters; ++c) s[c & 1] += (double)h[c * 16 + i];
+    const double per = (double)clusters * (cluster_ctas / 2) * kblocks;
+    fprintf(stderr, "  %-22s %9.1f | %9.1f\n", names[i], s[0] / per, s[1] / per);
   }
   return 0;
 }
@@ -572,6 +574,13 @@ static int launch_pair(const CUtensorMap& map_a, const CUtensorMap& map_b, const
   static int state = 0;
   return launch_pair_impl(tc::gemm_3xtf32_pair_kernel<kHi, kLo, false>, tc::gemm_3xtf32_pair_kernel<kHi, kLo, true>,
                           S::TOTAL, &state, kLo == 3 ? "pair<4,3>" : "pair<5,2>", map_a, map_b, p);
+}
+template <int kHi, int kLo>
+static int launch_pair_mc(const CUtensorMap& map_a, const CUtensorMap& map_b, const tc::PairParams& p) {
+  using S = tc::Smem<tc::PBN, kHi, kLo>;
+  static int state = 0;
+  return launch_pair_impl(tc::gemm_3xtf32_pair_kernel<kHi, kLo, false, 2>, tc::gemm_3xtf32_pair_kernel<kHi, kLo, true, 2>,
+                          S::TOTAL, &state, "pair_mc<4,3>", map_a, map_b, p, 4);
 }
 template <int kRaw>
 static int launch_pair_ts(const CUtensorMap& map_a, const CUtensorMap& map_b, const tc::PairParams& p) {
@@ -655,6 +664,14 @@ int gemm_tcgen05(const mdb_array* c, const mdb_array* a, const mdb_array* b, int
       q.tiles_m = (int)pm; q.tiles_n = (int)pn; q.group_m = 8;
       q.flags = g_gemm_flags;
       q.timing = nullptr;
+      if ((g_gemm_flags & 2097152) && pn % 2 == 0) {
+        // cluster of 4: two pairs on horizontally adjacent tiles share their A tiles by TMA multicast;
+        // a K-major A tile is fetched as two 64-row halves (one per pair), so its box is 32 x 64
+        CUtensorMap map_a_mc = maps[0];
+        if (!a_mn) MDB_TRY(make_map(&map_a_mc, (const float*)a->ptr, (int)K, (int)M, (int)a_pitch, 64, false));
+        q.tiles_n = (int)(pn / 2);
+        return launch_pair_mc<4, 3>(map_a_mc, maps[2], q);
+      }
       if (g_gemm_flags & 131072) return launch_pair_ts<5>(maps[0], maps[2], q);   // experimental: A in TMEM
       if (g_gemm_flags & 64) return launch_pair<5, 2>(maps[0], maps[2], q);   // A/B switches
       return launch_pair<4, 3>(maps[0], maps[2], q);

@@ -29,7 +29,7 @@ for (M, K, N) in [] if skip_check else [(256, 128, 256), (256, 512, 512), (512, 
         a, b, da, db = ops(M, K, N, layout)
         truth = a.astype(np.float64) @ b.astype(np.float64)
         res = {}
-        for name, fl in (("pair", 4 | 32), ("single", 4 | 16)):
+        for name, fl in (("pair", 4 | 32), ("single", 4 | 16), ("mc", 4 | 32 | 2097152)):
             check(lib.mdb_gemm_tune(fl))
             res[name] = np.abs(B.matmul(da, db).numpy() - truth).max()
         check(lib.mdb_gemm_tune(4 | 32))
@@ -37,9 +37,9 @@ for (M, K, N) in [] if skip_check else [(256, 128, 256), (256, 512, 512), (512, 
         dc = B.asarray(c0.copy())
         F._gemm(da, db, out=dc, accumulate=True)
         acc_err = np.abs(dc.numpy() - (c0 + truth)).max()
-        ok = res["pair"] <= 2 * res["single"] + 1e-6 and acc_err <= 2 * res["single"] + 1e-5
+        ok = res["pair"] <= 2 * res["single"] + 1e-6 and acc_err <= 2 * res["single"] + 1e-5 and res["mc"] <= 2 * res["single"] + 1e-6
         bad += (not ok)
-        print(f"{M}x{K}x{N} {layout}: pair {res['pair']:.2e} single {res['single']:.2e} acc {acc_err:.2e} {'ok' if ok else 'BAD'}", flush=True)
+        print(f"{M}x{K}x{N} {layout}: mc {res['mc']:.2e} pair {res['pair']:.2e} single {res['single']:.2e} acc {acc_err:.2e} {'ok' if ok else 'BAD'}", flush=True)
 print("correctness:", "ALL OK" if not bad else f"{bad} BAD", flush=True)
 if bad:
     sys.exit(1)
@@ -69,9 +69,9 @@ for name, M, K, N, layout in cases:
     b = B.asarray(rng.standard_normal((K, N), dtype=np.float32)) if layout[1] == "N" else B.asarray(rng.standard_normal((N, K), dtype=np.float32)).T
     out = []
     for rnd in range(1):
-        variants = (("pair43", 4 | 32), ("pair52", 4 | 32 | 64), ("single", 4 | 16))
+        variants = (("pair", 4 | 32), ("mc", 4 | 32 | 2097152), ("single", 4 | 16))
         if skip_check:
-            variants = (("pair43", 4 | 32), ("pair52", 4 | 32 | 64), ("single", 4 | 16))
+            variants = (("pair", 4 | 32), ("mc", 4 | 32 | 2097152))
         for nm, fl in variants:
             check(lib.mdb_gemm_tune(fl))
             t = timeit(a, b, 5)

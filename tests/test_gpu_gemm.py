@@ -130,15 +130,17 @@ def test_launch_is_tensor_core_for_large_shapes(B):
 
 
 @pytest.mark.parametrize("layout", ["NN", "NT", "TN", "TT"])
-def test_experimental_tmem_a_kernel_is_correct(B, layout):
-    """The A-operand-in-tensor-memory pair kernel (mdb_gemm_tune bit 17) is never selected by the
-    dispatcher (it is slower: single-buffered accumulator), but it must stay a correct reference."""
+@pytest.mark.parametrize("variant", [131072, 2097152])
+def test_experimental_pair_variants_are_correct(B, layout, variant):
+    """The A-operand-in-tensor-memory kernel (mdb_gemm_tune bit 17) and the 4-CTA-cluster kernel with
+    TMA-multicast A tiles (bit 21) are never selected by the dispatcher (both measured slower than the
+    plain pair kernel), but they must stay correct references."""
     from minidiff_b200.backend._lib import check, lib
 
     check(lib.mdb_gemm_config(2))
-    check(lib.mdb_gemm_tune(4 | 32 | 131072))
+    check(lib.mdb_gemm_tune(4 | 32 | variant))
     try:
-        for M, K, N in [(300, 260, 272), (1024, 1024, 768)]:
+        for M, K, N in [(300, 260, 272), (1024, 1024, 768), (520, 96, 1030)]:
             a, b, da, db = operands(B, M, K, N, layout, seed=M + N)
             np.testing.assert_allclose(B.matmul(da, db).numpy(), a @ b, rtol=1e-4, atol=1e-5 * np.sqrt(K))
     finally:
