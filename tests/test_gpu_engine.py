@@ -12,12 +12,61 @@ from conftest import GOLDEN, ulp_diff
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def md():
+REF_INSTALL = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
+def _reference_engine():
+    """The UNMODIFIED reference package (offline `pip install --target baseline/_ref /root/reference`,
+    git-ignored, shipped to the GPU box) with minidiff_b200.plugin selected through its own
+    `--backend` loader: its Tensor / ops / OpNode code then runs on this repo's device backend."""
+    import sys
+
+    if not os.path.isdir(os.path.join(REF_INSTALL, "minidiff")):
+        pytest.skip("baseline/_ref (offline install of the reference) not present")
+    root = os.path.dirname(REF_INSTALL.rstrip(os.sep))
+    for p in (os.path.join(os.path.dirname(root), "oracle", "_stubs"), REF_INSTALL):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    saved = sys.argv
+    sys.argv = [saved[0], "--backend", "minidiff_b200.plugin"]
+    try:
+        import minidiff as ref
+    finally:
+        sys.argv = saved
+    import minidiff_b200.plugin as plugin
+
+    plugin.assert_live(ref)
+    return ref
+
+
+@pytest.fixture(scope="module", params=["b200_engine", "reference_engine"])
+def md(request):
+    """Every engine test runs twice: with this repo's engine, and with the reference's own engine on
+    top of the same device backend (the drop-in boundary of SURVEY 8b, exercised on hardware)."""
+    if request.param == "reference_engine":
+        return _reference_engine()
     import minidiff_b200 as md
 
     md.backend.assert_live()
     return md
+
+
+def _submodule(md, name):
+    import importlib
+
+    return importlib.import_module(md.__name__ + "." + name)
+
+
+def _seed(md, n):
+    """device RNG of this repo's backend (the plugin exposes it to the reference engine too)"""
+    import minidiff_b200.backend as B
+
+    B.seed(n)
+
+
+def ours_only(md):
+    if md.__name__ != "minidiff_b200":
+        pytest.skip("exercises an extension of this repo's engine (not part of the reference API)")
 
 
 def close(got, want, rtol=1e-4, atol=1e-5):
@@ -195,7 +244,7 @@ def test_c4_full_size_properties(md):
     def grads_of(Xs, Ys):
         ps = [md.Tensor(p.copy(), allow_grad=True) for p in init]
         X, Y = md.Tensor(Xs), md.Tensor(Ys)
-        out = W.mlp_forward(X, ps)
+        out = mlp(md, X, ps)
         loss = md.mean((out - Y) ** 2)
         loss.backward()
         resid = md.sum(out - Y, axis=0).as_numpy().astype(np.float64)
@@ -405,9 +454,8 @@ FD_OPS = ["sin", "cos", "exp", "tanh", "sinh", "cosh", "absolute", "copy"]
 def test_first_order_fd_through_utils(md, name):
     """reference tests/test_ops.py:25-62 harness: loss = sum((0 - f(x))**2)/2, h = 1e-2,
     rtol 1e-3 / atol 1e-4, float64 inputs (NumPy-default dtype of md.randn)."""
-    from minidiff_b200.utils import compute_grads
-
-    md.backend.seed(3)
+    compute_grads = _submodule(md, "utils").compute_grads
+    _seed(md, 3)
     x = md.randn(2, 2, 2, 2, allow_grad=True)
     op = getattr(md, name)
 
@@ -420,9 +468,8 @@ def test_first_order_fd_through_utils(md, name):
 
 
 def test_fd_binary_broadcast_and_matmul(md):
-    from minidiff_b200.utils import compute_grads
-
-    md.backend.seed(5)
+    compute_grads = _submodule(md, "utils").compute_grads
+    _seed(md, 5)
     a, b = md.randn(3, 1, allow_grad=True), md.randn(1, 4, allow_grad=True)
     manual, auto = compute_grads(a, b, func=lambda p, q: md.sum(md.sin(p * q + p) ** 2), h=1e-3)
     for m_, a_ in zip(manual, auto):
@@ -483,7 +530,7 @@ def test_reuse_graph_cache_gives_same_grads(md):
         return x.grad.as_numpy()
 
     plain = step(md.Tensor(x_np, allow_grad=True))
-    with md.reuse_graph():
+    with _submodule(md, "caching").reuse_graph():
         c1 = step(md.Tensor(x_np, allow_grad=True))
         c2 = step(md.Tensor(x_np, allow_grad=True))
     np.testing.assert_array_equal(plain, c1)
@@ -493,8 +540,9 @@ def test_reuse_graph_cache_gives_same_grads(md):
 def test_custom_op_via_create_op_func(md):
     """README 'Custom Functions': as_minidiff + create_op_func on a backend function."""
     B = md.backend
-    softsign = md.create_unary_op_func(
-        forward_func=md.as_minidiff(lambda a: B.true_divide(a, B.add(B.absolute(a), 1))),
+    wr = _submodule(md, "ops.wrapping")       # the reference keeps the factories in ops/wrapping.py
+    softsign = wr.create_unary_op_func(
+        forward_func=wr.as_minidiff(lambda a: B.true_divide(a, B.add(B.absolute(a), 1))),
         grad=lambda x, grad: grad / (md.absolute(x) + 1) ** 2, op_name="softsign")
     x_np = np.linspace(-2, 2, 9, dtype=np.float32)
     x = md.Tensor(x_np, allow_grad=True)
@@ -505,6 +553,7 @@ def test_custom_op_via_create_op_func(md):
 
 
 def test_host_batch_feeder_pipeline_matches_resident_inputs(md):
+    ours_only(md)
     """e2e input pipeline (pinned host -> copy stream -> double-buffered device inputs) must feed
     exactly the bytes given, step after step, while uploads overlap compute."""
     from minidiff_b200 import workloads as W
@@ -526,6 +575,7 @@ def test_host_batch_feeder_pipeline_matches_resident_inputs(md):
 
 # ---------------------------------------------------------------- CUDA-graph capture
 def test_captured_graph_replays_c1_with_refreshed_inputs(md):
+    ours_only(md)
     """Capture forward + first-order backward of the README expression once, then replay it on new
     input values written IN PLACE: results must equal an eager evaluation bit for bit."""
     rng = np.random.default_rng(3)
@@ -557,6 +607,7 @@ def test_captured_graph_replays_c1_with_refreshed_inputs(md):
 
 
 def test_captured_training_step_matches_eager_and_pins_its_memory(md):
+    ours_only(md)
     """K replays of a captured MLP training step == K eager steps; memory allocated by OTHER work
     between replays never aliases the graph's buffers (private pool)."""
     from minidiff_b200 import workloads as W
@@ -585,6 +636,7 @@ def test_captured_training_step_matches_eager_and_pins_its_memory(md):
 
 
 def test_capture_refuses_readbacks(md):
+    ours_only(md)
     x = md.Tensor(np.ones((4, 4), np.float32), allow_grad=True)
 
     def bad():
