@@ -13,7 +13,8 @@ Headline line (one JSON object on stdout, rank 0):
   fwd_bwd (N=1)  = the single-GPU graph benchmarks of BASELINE.json: config 1 (README example, eager
                    vs one CUDA-graph replay, microseconds), config 2 (broadcast chain, GB/s vs HBM
                    roofline), config 3 (matmul fwd+bwd) and config 5 (Hessian-vector product), TFLOP/s
-                   vs the tensor roofline.
+                   vs the tensor roofline; c4_reference_engine_dropin = the same C4 step run by the
+                   UNMODIFIED reference engine with only --backend switched (baseline/_ref present).
   tensor roofline denominator = cuBLAS TF32 at 8192^3 measured in the same run (burst and sustained,
                    the way MEASURED_PEAKS.json measures bf16); pipe_frac = 3 * frac because a 3xTF32
                    GEMM issues three tensor-core MACs per fp32 product.
@@ -529,6 +530,58 @@ def bench_c1(dev, iters=200):
             "d2f_dx2": d2}
 
 
+def bench_c4_reference_engine(dev, steps, warmup):
+    """The pure drop-in number: the UNMODIFIED reference engine (baseline/_ref, its own Tensor /
+    OpNode / ops/definitions.py, out-of-place gradient accumulation, unfused backward) with only
+    `--backend minidiff_b200.plugin` switched, on the same C4 training step.  None if the offline
+    install of the reference is absent."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "minidiff")):
+        return None
+    for p in (os.path.join(ROOT, "oracle", "_stubs"), ref_dir):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    saved = sys.argv
+    sys.argv = [saved[0], "--backend", "minidiff_b200.plugin"]
+    try:
+        import minidiff as ref
+    finally:
+        sys.argv = saved
+    import minidiff_b200.plugin as plugin
+    from minidiff_b200 import workloads as W
+
+    plugin.assert_live(ref)
+    X_np, Y_np = W.mlp_data(GLOBAL_BATCH, DIMS[0], DIMS[-1], seed=1000)
+    params = [ref.Tensor(p, allow_grad=True) for p in W.mlp_params(DIMS)]
+    X, Y = ref.Tensor(X_np), ref.Tensor(Y_np)
+
+    def step():
+        h = X
+        for l in range(3):
+            h = h @ params[2 * l] + params[2 * l + 1]
+            if l < 2:
+                h = ref.where(h > 0, h, 0)
+        loss = ref.mean((h - Y) ** 2)
+        loss.backward()
+        with ref.no_grad():
+            for p in params:
+                p -= LR * p.grad
+        return loss
+
+    loss = warm_until_stable(dev, step, warmup)
+    e0, e1 = dev.event(), dev.event()
+    l0 = dev.launches()
+    dev.record(e0)
+    for _ in range(steps):
+        loss = step()
+    dev.record(e1)
+    dev.sync()
+    ms = dev.elapsed_ms(e0, e1) / steps
+    return {"workload": "C4 training step, UNMODIFIED reference engine + --backend minidiff_b200.plugin",
+            "ms_per_step": ms, "samples_per_s": GLOBAL_BATCH / (ms * 1e-3),
+            "launches_per_step": (dev.launches() - l0) / steps, "loss": float(loss.item())}
+
+
 def bench_c5(dev, steps, warmup, peaks, batch=8192):
     """BASELINE config 5: Hessian-vector product through a second-order graph of device ops."""
     md = dev.md
@@ -680,7 +733,8 @@ def main():
             line["fwd_bwd"] = {"c1_readme": bench_c1(dev),
                                "c2_broadcast_chain": bench_c2(dev, max(args.steps, 10), warmup, peaks),
                                "c3_matmul": bench_c3(dev, max(2, min(args.steps, 5)), warmup, peaks),
-                               "c5_hvp": bench_c5(dev, max(args.steps, 10), warmup, peaks)}
+                               "c5_hvp": bench_c5(dev, max(args.steps, 10), warmup, peaks),
+                               "c4_reference_engine_dropin": bench_c4_reference_engine(dev, 5, warmup)}
         if not args.skip_cpu:
             v, secs = cpu_mlp_samples_per_s(16384, 3)
             line["cpu_baseline"] = {
