@@ -39,7 +39,7 @@ sys.path.insert(0, ROOT)
 
 # ncu --set full capture of one C4 step at N=1 (profiles/r01_ncu_mlp_step_gemm_pair.md): DRAM bytes per GEMM
 # launch, and the algorithmic figure beside it (each operand read once + C written once, 8 GEMMs/step)
-GEMM_TRAFFIC_BYTES_PER_LAUNCH = 3.802e9
+GEMM_TRAFFIC_BYTES_PER_LAUNCH = 3.854e9
 GEMM_ALGORITHMIC_BYTES_PER_LAUNCH = (
     # fwd1, fwd2, fwd3 (X@W), dW3, dh2, dW2, dh1, dW1 at B=65536, D=(1024,4096,4096,1024)
     sum(4.0 * (m * k + k * n + m * n) for m, k, n in [
@@ -386,7 +386,7 @@ def bench_mlp(dev, dist, rank, world, steps, warmup, peaks):
             "pipe_frac": 3.0 * gemm_tflops / tf32_peak if tf32_peak else None,
             "traffic": GEMM_TRAFFIC_BYTES_PER_LAUNCH if world == 1 else None,
             "traffic_src": "dram__bytes_read.sum + dram__bytes_write.sum averaged over the 8 GEMM launches of one "
-                           "C4 step, profiles/r01_ncu_mlp_step_gemm_pair.md (same capture: tensor pipe 79-92 % "
+                           "C4 step, profiles/r01_ncu_mlp_step_gemm_pair.md (same capture: tensor pipe 83-94 % "
                            "active at the power-capped 1.55-1.68 GHz)",
             "algorithmic_bytes_per_launch": GEMM_ALGORITHMIC_BYTES_PER_LAUNCH if world == 1 else None,
             "launches": int(gemm_n), "avg_launch_ms": gemm_ms / gemm_n if gemm_n else None,
