@@ -166,6 +166,35 @@ int mdb_gemm(const mdb_array* c, const mdb_array* a, const mdb_array* b, int acc
 int mdb_gemm_tune(int flags);                     /* kernel tuning switches for A/B measurements   */
 int mdb_gemm_config(int force_path);              /* 0 auto, 1 CUDA-core kernel only, 2 tensor-core
                                                      kernel only (tests) */
+/* which kernel the GEMM launches took since the last reset: counts[MDB_GEMM_NPATHS], indexed by the
+ * enum below (parity tests at BASELINE dims assert that every GEMM of the step ran on the CTA-pair
+ * tcgen05 kernel the benchmark measures) */
+enum { MDB_GEMM_PATH_SIMT = 0,        /* fp32 CUDA-core kernel (small / odd shapes)                 */
+       MDB_GEMM_PATH_TC_SINGLE = 1,   /* tcgen05, one CTA per 128x128 tile, TMA reads operands in place */
+       MDB_GEMM_PATH_TC_PRESPLIT = 2, /* tcgen05 single-CTA after a hi/lo gather pre-pass           */
+       MDB_GEMM_PATH_TC_PAIR = 3,     /* tcgen05 cta_group::2, 256x256 tiles, whole tiles per pair  */
+       MDB_GEMM_PATH_TC_PAIR_STREAMK = 4, /* same kernel, k-range split across pairs (stream-K)     */
+       MDB_GEMM_NPATHS = 8 };
+int mdb_gemm_stats(uint64_t* counts, int reset);
+/* measurement knobs of the CTA-pair kernel's planner (-1 = automatic): tile order, L2 eviction hints
+ * (0 none, 1 evict_first, 2 evict_last), stream-K (0 never, 1 whenever legal) */
+enum { MDB_GEMM_KNOB_RASTER = 0, MDB_GEMM_KNOB_GROUP = 1, MDB_GEMM_KNOB_HINT_A = 2, MDB_GEMM_KNOB_HINT_B = 3,
+       MDB_GEMM_KNOB_HINT_C = 4, MDB_GEMM_KNOB_STREAMK = 5, MDB_GEMM_KNOB_L2_BUDGET_MB = 6 };
+int mdb_gemm_knob(int knob, int value);
+/* plan of the most recent CTA-pair launch: clusters, raster, group, dp_tiles, sk_clusters, sk_share,
+ * hints (100*A + 10*B + C), tiles */
+int mdb_gemm_last_plan(int* out8);
+/* GEMM with a fused epilogue, the device op behind a user-defined stateful op (the reference's
+ * create_stateful_op_func / OpClass, ops/wrapping.py:47-76,181-217 -- e.g. linear_relu):
+ *   C (+)= mask( relu?( A@B + bias? ) )      bias: fp32 [N] or NULL;  relu: where(v > 0, v, 0);
+ *   mask_src: fp32 [M, N] row-major or NULL, multiplies by (mask_src > 0) -- the ReLU backward
+ *   `grad * (y > 0)` applied where the gradient GEMM produces it.
+ * Each step rounds like the separate backend call it replaces (add / where / multiply), so the
+ * result is bit-identical to matmul -> add -> where (resp. matmul -> multiply by the mask).
+ * Returns MDB_ENOTSUP when the problem cannot run on the CTA-pair tensor-core kernel (callers
+ * then issue the unfused chain). */
+int mdb_gemm_fused(const mdb_array* c, const mdb_array* a, const mdb_array* b, int accumulate,
+                   const mdb_array* bias, int relu, const mdb_array* mask_src);
 
 /* integer-array indexing (getitem / `a[key] = v` / index_add with array keys:
  * backend/numpy.py:73-75,105; tensor.py:376-379) over the leading axis:

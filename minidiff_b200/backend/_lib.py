@@ -94,6 +94,10 @@ _SIGS = {
     "mdb_gemm": (C.c_int, [_A, _A, _A, C.c_int]),
     "mdb_gemm_config": (C.c_int, [C.c_int]),
     "mdb_gemm_tune": (C.c_int, [C.c_int]),
+    "mdb_gemm_stats": (C.c_int, [_P(C.c_uint64), C.c_int]),
+    "mdb_gemm_knob": (C.c_int, [C.c_int, C.c_int]),
+    "mdb_gemm_last_plan": (C.c_int, [_P(C.c_int)]),
+    "mdb_gemm_fused": (C.c_int, [_A, _A, _A, C.c_int, _A, C.c_int, _A]),
     "mdb_gather_rows": (C.c_int, [_A, _A, _A]),
     "mdb_scatter_rows": (C.c_int, [_A, _A, _A, C.c_int]),
     "mdb_random": (C.c_int, [_A, C.c_int, C.c_uint64, C.c_uint64]),

@@ -594,6 +594,33 @@ def _gemm(a: DeviceArray, b: DeviceArray, out=None, accumulate=False) -> DeviceA
     return out
 
 
+def _gemm_fused(a: DeviceArray, b: DeviceArray, bias=None, relu=False, mask_src=None, out=None,
+                accumulate=False):
+    """out (+)= mask(relu?(a @ b + bias?)) in ONE launch of the CTA-pair tcgen05 kernel (C ABI
+    mdb_gemm_fused).  Returns None when the problem cannot run there (small / unaligned shapes):
+    the caller then issues the unfused chain of backend calls."""
+    if a.shape[1] != b.shape[0]:
+        raise ValueError(
+            f"matmul: Input operand 1 has a mismatch in its core dimension 0, with gufunc signature "
+            f"(n?,k),(k,m?)->(n?,m?) (size {b.shape[0]} is different from {a.shape[1]})")
+    m, n = a.shape[0], b.shape[1]
+    if m <= 128 or n <= 128 or a.shape[1] < 32 or m * n * a.shape[1] < (1 << 21):
+        return None
+    if bias is not None and not (bias.dtype == F32 and bias.shape == (n,) and bias.estrides == (1,)):
+        return None
+    if mask_src is not None and not (mask_src.dtype == F32 and mask_src.shape == (m, n) and mask_src.estrides[1] == 1):
+        return None
+    if out is None:
+        out = DeviceArray.empty((m, n), F32)
+    rc = lib.mdb_gemm_fused(_byref(out.d), _byref(a.d), _byref(b.d), 1 if accumulate else 0,
+                            _byref(bias.d) if bias is not None else None, 1 if relu else 0,
+                            _byref(mask_src.d) if mask_src is not None else None)
+    if rc == _lib.ENOTSUP:
+        return None
+    check(rc)
+    return out
+
+
 def matmul(x, y, **_kw):
     x, y = asarray(x), asarray(y)
     if x.ndim == 0 or y.ndim == 0:

@@ -5,9 +5,14 @@
 
 namespace mdb {
 
-int gemm_tcgen05(const mdb_array* c, const mdb_array* a, const mdb_array* b, int accumulate);
+int gemm_tcgen05(const mdb_array* c, const mdb_array* a, const mdb_array* b, int accumulate, const GemmEpilogue* epi);
+extern int g_last_plan[8];
+extern int g_knob_raster, g_knob_group, g_knob_hint_a, g_knob_hint_b, g_knob_hint_c, g_knob_streamk, g_knob_l2_budget_mb;
 static int g_force_path = 0;
 extern int g_gemm_flags;
+// launches per GEMM kernel since the last reset (mdb_gemm_stats): tests assert with it that a
+// workload really ran on the kernel it is meant to cover (a silent fallback cannot hide)
+uint64_t g_gemm_path[MDB_GEMM_NPATHS] = {};
 
 // 64x64 output tile per CTA, K step 16, 4x4 micro-tile per thread; operands addressed through
 // (row, col) element strides so NN / NT / TN views need no copies.
@@ -78,6 +83,7 @@ static int gemm_simt(const mdb_array* c, const mdb_array* a, const mdb_array* b,
         a->strides[1], (const float*)b->ptr, b->strides[0], b->strides[1], (float*)c->ptr,
         c->strides[0], c->strides[1]);
   MDB_CHECK_LAUNCH();
+  ++g_gemm_path[MDB_GEMM_PATH_SIMT];
   return 0;
 }
 
@@ -93,9 +99,73 @@ int mdb_gemm_config(int force_path) {
   return 0;
 }
 
+int mdb_gemm_stats(uint64_t* counts, int reset) {
+  if (counts)
+    for (int i = 0; i < MDB_GEMM_NPATHS; ++i) counts[i] = g_gemm_path[i];
+  if (reset)
+    for (int i = 0; i < MDB_GEMM_NPATHS; ++i) g_gemm_path[i] = 0;
+  return 0;
+}
+
+int mdb_gemm_last_plan(int* out8) {
+  for (int i = 0; i < 8; ++i) out8[i] = g_last_plan[i];
+  return 0;
+}
+
 int mdb_gemm_tune(int flags) {
   g_gemm_flags = flags;
   return 0;
+}
+
+int mdb_gemm_knob(int knob, int value) {
+  switch (knob) {
+    case MDB_GEMM_KNOB_RASTER: g_knob_raster = value; break;
+    case MDB_GEMM_KNOB_GROUP: g_knob_group = value; break;
+    case MDB_GEMM_KNOB_HINT_A: g_knob_hint_a = value; break;
+    case MDB_GEMM_KNOB_HINT_B: g_knob_hint_b = value; break;
+    case MDB_GEMM_KNOB_HINT_C: g_knob_hint_c = value; break;
+    case MDB_GEMM_KNOB_STREAMK: g_knob_streamk = value; break;
+    case MDB_GEMM_KNOB_L2_BUDGET_MB: g_knob_l2_budget_mb = value > 0 ? value : 40; break;
+    default: return set_error(MDB_EINVAL, "unknown GEMM knob %d", knob);
+  }
+  return 0;
+}
+
+static int check_gemm_args(const mdb_array* c, const mdb_array* a, const mdb_array* b) {
+  MDB_REQUIRE(a && b && c && a->ptr && b->ptr && c->ptr, "gemm: device arrays required");
+  MDB_REQUIRE(a->ndim == 2 && b->ndim == 2 && c->ndim == 2, "gemm: operands must be 2-D");
+  MDB_REQUIRE(a->dtype == MDB_F32 && b->dtype == MDB_F32 && c->dtype == MDB_F32,
+              "gemm: fp32 operands required");
+  if (a->shape[1] != b->shape[0])
+    return set_error(MDB_EINVAL, "matmul: Input operand 1 has a mismatch in its core dimension 0, "
+                     "with gufunc signature (n?,k),(k,m?)->(n?,m?) (size %lld is different from %lld)",
+                     (long long)b->shape[0], (long long)a->shape[1]);
+  MDB_REQUIRE(c->shape[0] == a->shape[0] && c->shape[1] == b->shape[1], "gemm: bad output shape");
+  MDB_REQUIRE(a->shape[0] < (1ll << 31) && a->shape[1] < (1ll << 31) && b->shape[1] < (1ll << 31),
+              "gemm: extents must fit in int32");
+  return 0;
+}
+
+int mdb_gemm_fused(const mdb_array* c, const mdb_array* a, const mdb_array* b, int accumulate,
+                   const mdb_array* bias, int relu, const mdb_array* mask_src) {
+  MDB_TRY(ensure_init());
+  MDB_TRY(check_gemm_args(c, a, b));
+  MDB_REQUIRE(c->shape[0] > 0 && c->shape[1] > 0 && a->shape[1] > 0, "gemm_fused: empty operands");
+  GemmEpilogue epi = {nullptr, relu ? 1 : 0, nullptr, 0};
+  if (bias) {
+    MDB_REQUIRE(bias->ptr && bias->dtype == MDB_F32 && bias->ndim == 1 && bias->shape[0] == c->shape[1] &&
+                bias->strides[0] == 1, "gemm_fused: bias must be a contiguous fp32 vector of length N");
+    epi.bias = (const float*)bias->ptr;
+  }
+  if (mask_src) {
+    MDB_REQUIRE(mask_src->ptr && mask_src->dtype == MDB_F32 && mask_src->ndim == 2 &&
+                mask_src->shape[0] == c->shape[0] && mask_src->shape[1] == c->shape[1] && mask_src->strides[1] == 1,
+                "gemm_fused: mask source must be a row-major fp32 matrix of C's shape");
+    epi.mask_src = (const float*)mask_src->ptr;
+    epi.ld_mask = mask_src->strides[0];
+  }
+  ProfScope prof(PROF_GEMM, 2.0 * (double)a->shape[0] * (double)a->shape[1] * (double)b->shape[1]);
+  return gemm_tcgen05(c, a, b, accumulate, &epi);
 }
 
 int mdb_gemm(const mdb_array* c, const mdb_array* a, const mdb_array* b, int accumulate) {
@@ -115,7 +185,7 @@ int mdb_gemm(const mdb_array* c, const mdb_array* a, const mdb_array* b, int acc
   if (a->shape[1] == 0) return accumulate ? 0 : mdb_fill(c, 0.0);
   ProfScope prof(PROF_GEMM, 2.0 * (double)a->shape[0] * (double)a->shape[1] * (double)b->shape[1]);
   if (g_force_path != 1) {
-    int rc = gemm_tcgen05(c, a, b, accumulate);
+    int rc = gemm_tcgen05(c, a, b, accumulate, nullptr);
     if (rc == 0) return 0;
     if (rc != MDB_ENOTSUP || g_force_path == 2) return rc;
   }

@@ -1,17 +1,16 @@
 // CTA-pair (cta_group::2) 3xTF32 GEMM kernel.  Included by gemm_tcgen05.cu inside namespace mdb::tc
-// (shares Params / Smem / Ring / tile_coords with the single-CTA kernel defined there).
+// (shares Smem / Ring with the single-CTA kernel defined there).
 #pragma once
 
 // =====================================================================================================
 // CTA-PAIR kernel (cta_group::2): one 256 x 256 output tile per pair of SMs, RAW mode only.
 //
-// Why: at M=128, N=128 a kind::tf32 MMA reads 8 KB of shared memory per 64 tensor-core cycles -- the
-// whole 128 B/clk of an SM -- and the TMA writes (32 KB per k-block) and the converter warps (64 KB per
-// k-block) compete for the same port: ncu showed the single-CTA kernel at 47-54 % tensor-pipe
-// utilisation with the LSU shared-memory share at 43 % (profiles/r01_gemm_raw_ncu.md).  As a pair,
-// each SM still stages a 128-row A tile and a 128-row B tile per k-block (same 32 KB raw + 32 KB lo),
-// but every MMA is 256 x 256 x 8: each SM's tensor core works 128 cycles on the same 8 KB, so the
-// operand traffic per flop halves (MMA 64 B/clk + converters 42 + TMA 21 = ~125 B/clk).
+// Why pairs: at M=128, N=128 a kind::tf32 MMA reads 8 KB of shared memory per 64 tensor-core cycles --
+// the whole 128 B/clk of an SM -- and the TMA writes (32 KB per k-block) and the converter warps (64 KB
+// per k-block) compete for the same port: the single-CTA kernel measured 47-54 % tensor-pipe
+// utilisation.  As a pair, each SM still stages a 128-row A tile and a 128-row B tile per k-block
+// (32 KB raw + 32 KB lo), but every MMA is 256 x 256 x 8: each SM's tensor core works 128 cycles on
+// the same 8 KB, so the operand traffic per flop halves (MMA 64 B/clk + converters 42 + TMA 21).
 //
 //   CTA r of the pair loads   A rows  [m0 + 128 r, +128)   and   B rows (n) [n0 + 128 r, +128)
 //   and owns accumulator rows [m0 + 128 r, +128) x all 256 columns in ITS tensor memory.
@@ -26,22 +25,31 @@
 // .release.cluster form is ~1000 cycles slower and what makes the plain one sufficient here).
 // 512 threads: control warpgroup (TMA, MMA, TMEM alloc), 2 epilogue warpgroups (128 columns each,
 // 128 fp32 promotion registers per thread), 1 converter warpgroup; setmaxnreg 40 / 200 / 64 from a
-// launch value of 128.  setmaxnreg.inc only draws on registers that other warps RELEASED with .dec
-// (a first version launched 640 threads at 96 and asked for more than was released: it hung in .inc),
+// launch value of 128.  setmaxnreg.inc only draws on registers that other warps RELEASED with .dec,
 // so the shares balance: released 88*128 + 64*128 = 19456 >= requested 72*256 = 18432.
 //
-// Where the time goes (MDB_GEMM_TIMING=1 build, 8192^3, cycles per k-block; the MMAs of one k-block
-// need 12 x 128 = 1536 tensor-core cycles):   period 1805 = 85 % tensor-pipe utilisation
-//   converter: work 1216 + fence/arrive 253 + waits 185      MMA warp: waits for lo_full 612
-//   TMA producer: waits for hi_empty 1135 (never the bottleneck)
-// The converter is throughput-bound on the shared-memory port, which the three clients share:
-// tensor core 768 wavefronts of 128 B per k-block, converter 256 (LDS) + 256 (STS), TMA writes 256
-// = 1536 wavefronts per k-block at 1 wavefront/clk -- the same 1536 cycles the MMAs need.  The
-// kernel sits at that shared-memory roofline; software-pipelining the converter loads, deeper
-// rings (<5,2>, <6,1>) and dropping two thirds of the MMAs all leave the period unchanged.
+// Work distribution (round 2).  A cluster's work is a list of SEGMENTS (tile, kb0, kb1):
+//   * data-parallel part: tiles [0, dp_tiles) whole, round-robin over the clusters (dp_tiles is a
+//     multiple of the cluster count: full waves only);
+//   * stream-K part: the k-blocks of the remaining tiles, linearised tile-major, are cut into
+//     `sk_share`-sized contiguous ranges, one per cluster (c < sk_clusters).  A range may end inside a
+//     tile and the next cluster continues it.  The cluster whose segment STARTS a tile (kb0 == 0)
+//     owns it: clusters that continue the tile (kb0 > 0; always their FIRST segment, so it is
+//     finished early) deposit their fp32 register sums in a per-cluster slot of a global workspace
+//     and raise a flag per epilogue warp; the owner -- whose partial segment is its LAST one -- adds
+//     the slots in cluster order (deterministic) and stores.  A wait only ever targets the first
+//     segment of a higher-numbered cluster, which never waits itself, so the scheme cannot deadlock
+//     even when not all clusters are co-resident.
+//   This removes the wave-quantisation loss of the last, partially filled wave (dW2 of the C4 step:
+//   256 tiles on 74 clusters = 3.46 waves -> 3 + 34 tiles split two ways = 3.5 instead of 4).
+// Tile order (raster): groups of `group` tile-rows walked column by column (raster 0) or groups of
+// `group` tile-columns walked row by row (raster 1), so that the clusters of a wave share few
+// distinct operand panels; TMA loads and C stores carry L2 eviction hints chosen by the host.
+// Fused epilogue (linear_relu): C = relu?( A@B + bias? ) * (mask_src > 0)?
 constexpr int kPairThreads = 512;
 constexpr int kPairConvWarps = 4, kPairEpiWarps = 8;
 constexpr int PBN = 128;          // B rows staged per CTA; the UMMA N is 2 * PBN
+constexpr int kSkSlotFloats = 2 * kPairEpiWarps * 128 * 32;   // one cluster's 256 x 256 fp32 partial tile
 
 struct PairParams {
   int M, N, K;
@@ -49,7 +57,17 @@ struct PairParams {
   float* C;
   int64_t ldc;
   int accumulate;
-  int tiles_m, tiles_n, group_m;   // in 256 x 256 pair tiles
+  int tiles_m, tiles_n;            // in 256 x 256 pair tiles
+  int raster, group;               // tile order, see tile_coords_pair
+  int dp_tiles;                    // tiles [0, dp_tiles): whole tiles, round-robin
+  int sk_clusters, sk_share;       // stream-K part: clusters [0, sk_clusters) take sk_share k-blocks each
+  float* sk_partials;              // [clusters][2 CTAs][8 warps][128][32]
+  uint32_t* sk_flags;              // [clusters][2 CTAs][8 warps]
+  const float* bias;               // epilogue: + bias[col] (nullable)
+  int relu;                        // epilogue: max(v, 0) with where(v > 0, v, 0) semantics
+  const float* mask_src;           // epilogue: * (mask_src[row, col] > 0) (nullable)
+  int64_t ld_mask;
+  int hint_a, hint_b, hint_c;      // L2 eviction hints: 0 none, 1 evict_first, 2 evict_last
   int flags;
   unsigned long long* timing;      // MDB_GEMM_TIMING=1: per-CTA stall-cycle counters (16 per CTA), else null
 };
@@ -57,13 +75,82 @@ struct PairParams {
 #define MDB_T0() (kTiming ? clock64() : 0ll)
 #define MDB_TACC(var, t0) do { if (kTiming) var += clock64() - (t0); } while (0)
 
-// kMc = 1: cluster of 2 (one pair).  kMc = 2: cluster of 4 = two pairs working on horizontally
-// adjacent tiles (same A rows): every A tile is fetched from L2 ONCE and TMA-multicast into both pairs
-// (each of the two CTAs that need it loads half of it for both), which cuts the L2 -> SM traffic by
-// a quarter.  A slot may only be refilled when BOTH pairs are done with it: hi_empty counts one
-// commit per pair, multicast to all four CTAs.
-template <int kHi, int kLo, bool kTiming, int kMc = 1>
-__global__ void __cluster_dims__(2 * kMc, 1, 1) __launch_bounds__(kPairThreads, 1)
+struct Segment { int tile, kb0, kb1; };
+
+// Every role of the kernel walks the same segment list of its cluster.
+struct WorkIter {
+  int next_dp, step, dp_tiles, num_k;
+  long long lin, lin_end;
+  __device__ __forceinline__ WorkIter(const PairParams& p, int cluster, int nclusters, int num_k_) {
+    next_dp = cluster; step = nclusters; dp_tiles = p.dp_tiles; num_k = num_k_;
+    lin = lin_end = 0;
+    if (cluster < p.sk_clusters) {
+      const long long total = (long long)(p.tiles_m * p.tiles_n - p.dp_tiles) * num_k;
+      lin = (long long)cluster * p.sk_share;
+      lin_end = lin + p.sk_share < total ? lin + p.sk_share : total;
+    }
+  }
+  __device__ __forceinline__ bool next(Segment& s) {
+    if (next_dp < dp_tiles) {
+      s.tile = next_dp; s.kb0 = 0; s.kb1 = num_k;
+      next_dp += step;
+      return true;
+    }
+    if (lin < lin_end) {
+      const int t = (int)(lin / num_k);
+      s.kb0 = (int)(lin - (long long)t * num_k);
+      const long long left = lin_end - lin;
+      s.kb1 = (long long)s.kb0 + left < num_k ? s.kb0 + (int)left : num_k;
+      s.tile = dp_tiles + t;
+      lin += s.kb1 - s.kb0;
+      return true;
+    }
+    return false;
+  }
+};
+
+__device__ __forceinline__ void tile_coords_pair(const PairParams& p, int t, int& m_blk, int& n_blk) {
+  if (p.raster == 0) {        // groups of `group` tile-rows, walked column by column (m fastest)
+    const int per_group = p.group * p.tiles_n;
+    const int g = t / per_group, r = t - g * per_group;
+    const int rows = min(p.group, p.tiles_m - g * p.group);
+    m_blk = g * p.group + (r % rows);
+    n_blk = r / rows;
+  } else {                    // groups of `group` tile-columns, walked row by row (n fastest)
+    const int per_group = p.group * p.tiles_m;
+    const int g = t / per_group, r = t - g * per_group;
+    const int cols = min(p.group, p.tiles_n - g * p.group);
+    n_blk = g * p.group + (r % cols);
+    m_blk = r / cols;
+  }
+}
+
+__device__ __forceinline__ uint64_t l2_policy(int hint) {
+  uint64_t pol = 0;
+  if (hint == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  else if (hint == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <int kHi, int kLo, bool kTiming>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                         const PairParams p) {
   using S = Smem<PBN, kHi, kLo>;
@@ -79,23 +166,17 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t crank = cluster_ctarank();            // rank in the cluster (0..2*kMc-1)
-  const uint32_t rank = crank & 1;                      // rank inside the CTA pair
-  const uint32_t pair = crank >> 1;                     // which pair of the cluster (kMc = 2)
-  const uint32_t leader = crank & ~1u;                  // cluster rank of this pair's leader CTA
-  const int first_tile = (int)cluster_id_x(), tile_step = (int)num_clusters_x();
+  const uint32_t rank = cluster_ctarank();              // rank inside the CTA pair; 0 = leader
+  const int cluster = (int)cluster_id_x(), nclusters = (int)num_clusters_x();
   constexpr uint32_t kTmemCols = 512;            // two 256-column accumulator stages
-  const int num_tiles = p.tiles_m * p.tiles_n;
   const int num_k = (p.K + BK - 1) / BK;
-  Params tp;                                     // tile_coords() only reads these three
-  tp.tiles_m = p.tiles_m; tp.tiles_n = p.tiles_n; tp.group_m = p.group_m;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kHi; ++s) { mbar_init(&hi_full[s], 1); mbar_init(&hi_empty[s], kMc); }
+    for (int s = 0; s < kHi; ++s) { mbar_init(&hi_full[s], 1); mbar_init(&hi_empty[s], 1); }
     for (int s = 0; s < kLo; ++s) { mbar_init(&lo_full[s], 2 * kPairConvWarps); mbar_init(&lo_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 2 * kPairEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -118,14 +199,16 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     // ===================================== TMA producer (both CTAs) ==========================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (lane == 0) {
+      const uint64_t pol_a = l2_policy(p.hint_a), pol_b = l2_policy(p.hint_b);
       Ring hi;
       long long w_empty = 0, t_all = MDB_T0();
-      for (int t = first_tile; t < num_tiles; t += tile_step) {
+      Segment s;
+      for (WorkIter w(p, cluster, nclusters, num_k); w.next(s);) {
         int m_blk, n_blk;
-        tile_coords(tp, t, m_blk, n_blk);
-        const int m0 = m_blk * 256 + (int)rank * BM, n0 = (n_blk * kMc + (int)pair) * 256 + (int)rank * PBN;
-        for (int kb = 0; kb < num_k; ++kb) {
-          const int k0 = (kTiming && (p.flags & 4096)) ? (kb & 7) * BK : kb * BK;   // 4096: diagnostic, L2-resident k range
+        tile_coords_pair(p, s.tile, m_blk, n_blk);
+        const int m0 = m_blk * 256 + (int)rank * BM, n0 = n_blk * 256 + (int)rank * PBN;
+        for (int kb = s.kb0; kb < s.kb1; ++kb) {
+          const int k0 = kb * BK;
           const long long tw = MDB_T0();
           mbar_wait(&hi_empty[hi.slot], hi.phase ^ 1);
           MDB_TACC(w_empty, tw);
@@ -133,25 +216,16 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
           uint64_t* hbar = &hi_full[hi.slot];
           mbar_expect_tx(hbar, S::SLOT_BYTES);
           if (!p.a_mn_major) {
-            if constexpr (kMc == 1) {
-              tma_load_2d(a_hi, &map_a, hbar, k0, m0);
-            } else {               // this CTA fetches rows [64 pair, +64) of the tile for both pairs (box = 32 x 64)
-              tma_load_2d_mc(a_hi + pair * (64 * 128), &map_a, hbar, k0, m0 + 64 * (int)pair,
-                             (uint16_t)((1u << rank) | (1u << (rank + 2))));
-            }
+            tma_load_2d_hint(a_hi, &map_a, hbar, k0, m0, pol_a);
           } else {
 #pragma unroll
-            for (int c = 0; c < BM / 32; ++c) {
-              if constexpr (kMc == 1) tma_load_2d(a_hi + c * 4096, &map_a, hbar, m0 + 32 * c, k0);
-              else if ((c >> 1) == (int)pair)     // two of the four 32-column boxes each, for both pairs
-                tma_load_2d_mc(a_hi + c * 4096, &map_a, hbar, m0 + 32 * c, k0, (uint16_t)((1u << rank) | (1u << (rank + 2))));
-            }
+            for (int c = 0; c < BM / 32; ++c) tma_load_2d_hint(a_hi + c * 4096, &map_a, hbar, m0 + 32 * c, k0, pol_a);
           }
           if (!p.b_mn_major) {
-            tma_load_2d(b_hi, &map_b, hbar, k0, n0);
+            tma_load_2d_hint(b_hi, &map_b, hbar, k0, n0, pol_b);
           } else {
 #pragma unroll
-            for (int c = 0; c < PBN / 32; ++c) tma_load_2d(b_hi + c * 4096, &map_b, hbar, n0 + 32 * c, k0);
+            for (int c = 0; c < PBN / 32; ++c) tma_load_2d_hint(b_hi + c * 4096, &map_b, hbar, n0 + 32 * c, k0, pol_b);
           }
           hi.advance(kHi);
         }
@@ -162,7 +236,6 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     // ===================================== MMA issuer (leader CTA only) ======================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (rank == 0) {
-      const uint16_t pair_mask = (uint16_t)(3u << (2 * pair)), all_mask = (uint16_t)((1u << (2 * kMc)) - 1);
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn_major << 15) |
                              ((uint32_t)p.b_mn_major << 16) | ((uint32_t)((2 * PBN) >> 3) << 17) |
                              ((uint32_t)(256 >> 4) << 24);
@@ -174,10 +247,11 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
       int acc = 0;
       uint32_t acc_phase = 0;
       long long w_lo = 0, w_tmem = 0, t_all = MDB_T0();
-      for (int t = first_tile; t < num_tiles; t += tile_step) {
-        for (int kb = 0; kb < num_k; ++kb) {
-          const bool chunk_start = (kb % kChunk) == 0;
-          const bool chunk_end = ((kb + 1) % kChunk) == 0 || kb == num_k - 1;
+      Segment s;
+      for (WorkIter w(p, cluster, nclusters, num_k); w.next(s);) {
+        for (int kb = s.kb0; kb < s.kb1; ++kb) {
+          const bool chunk_start = ((kb - s.kb0) % kChunk) == 0;
+          const bool chunk_end = ((kb - s.kb0 + 1) % kChunk) == 0 || kb == s.kb1 - 1;
           if (chunk_start) {
             const long long tw = MDB_T0();
             mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1);   // both CTAs drained this accumulator
@@ -198,34 +272,13 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
               const uint64_t da_lo = make_desc(a_lo + k * a_kstep, a_lbo, a_sbo, a_lt);
               const uint64_t db_hi = make_desc(b_hi + k * b_kstep, b_lbo, b_sbo, b_lt);
               const uint64_t db_lo = make_desc(b_lo + k * b_kstep, b_lbo, b_sbo, b_lt);
-              if (kTiming && (p.flags & 65536)) {
-                // diagnostic (wrong results): A operand from tensor memory -- what would the period be
-                // if the tensor core did not read the A tiles from shared memory?
-                const uint32_t ta = tmem_base + (acc ^ 1) * 256 + k * 8;
-                umma_tf32_pair_ts(tmem_d, ta, db_hi, idesc, 1);
-                umma_tf32_pair_ts(tmem_d, ta, db_lo, idesc, 1);
-                umma_tf32_pair_ts(tmem_d, ta + 32, db_hi, idesc, 1);
-                continue;
-              }
-              if (kTiming && (p.flags & (128 | 256))) {
-                // diagnostic build only (results are wrong): 128 = alternate the two TMEM buffers
-                // between consecutive MMAs (no back-to-back dependency on one accumulator),
-                // 256 = issue only hi*hi (one MMA per k-step)
-                const uint32_t alt = (p.flags & 128) ? tmem_base + (acc ^ 1) * 256 : tmem_d;
-                if (!(p.flags & 256)) {
-                  umma_tf32_pair(tmem_d, da_lo, db_hi, idesc, 1);
-                  umma_tf32_pair(alt, da_hi, db_lo, idesc, 1);
-                }
-                umma_tf32_pair((k & 1) ? alt : tmem_d, da_hi, db_hi, idesc, 1);
-                continue;
-              }
               umma_tf32_pair(tmem_d, da_lo, db_hi, idesc, !(chunk_start && k == 0));
               umma_tf32_pair(tmem_d, da_hi, db_lo, idesc, 1);
               umma_tf32_pair(tmem_d, da_hi, db_hi, idesc, 1);
             }
-            umma_commit_pair(&lo_empty[lo.slot], pair_mask);
-            umma_commit_pair(&hi_empty[hi.slot], all_mask);       // kMc = 2: both pairs must release an A slot
-            if (chunk_end) umma_commit_pair(&tmem_full[acc], pair_mask);
+            umma_commit_pair(&lo_empty[lo.slot]);
+            umma_commit_pair(&hi_empty[hi.slot]);
+            if (chunk_end) umma_commit_pair(&tmem_full[acc]);
           }
           __syncwarp();
           hi.advance(kHi);
@@ -245,8 +298,9 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     const int t = threadIdx.x - (4 + kPairEpiWarps) * 32;
     Ring hi, lo;
     long long w_hi = 0, w_lo = 0, t_work = 0, t_sig = 0, t_all = MDB_T0();
-    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
-      for (int kb = 0; kb < num_k; ++kb) {
+    Segment s;
+    for (WorkIter w(p, cluster, nclusters, num_k); w.next(s);) {
+      for (int kb = s.kb0; kb < s.kb1; ++kb) {
         const long long ta = MDB_T0();
         mbar_wait(&hi_full[hi.slot], hi.phase);
         MDB_TACC(w_hi, ta);
@@ -268,35 +322,30 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
                          : "=f"(dstv[j].x), "=f"(dstv[j].y), "=f"(dstv[j].z), "=f"(dstv[j].w)
                          : "r"(src + (t + (bt * kBatch + j) * kConv) * 16));
         };
-        if (!(kTiming && (p.flags & 512))) {                       // 512: diagnostic, no conversion
-          load_batch(0, v[0]);
+        load_batch(0, v[0]);
 #pragma unroll
-          for (int bt = 0; bt < kBatches; ++bt) {
-            if (bt + 1 < kBatches) load_batch(bt + 1, v[(bt + 1) & 1]);
+        for (int bt = 0; bt < kBatches; ++bt) {
+          if (bt + 1 < kBatches) load_batch(bt + 1, v[(bt + 1) & 1]);
 #pragma unroll
-            for (int j = 0; j < kBatch; ++j) {
-              const float4 x = v[bt & 1][j];
-              float e[4] = {x.x, x.y, x.z, x.w};
+          for (int j = 0; j < kBatch; ++j) {
+            const float4 x = v[bt & 1][j];
+            float e[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float h = __uint_as_float(__float_as_uint(e[i]) & 0xFFFFE000u);   // what the MMA sees
-                if (p.flags & 4) e[i] = __fsub_rn(e[i], h);
-                else e[i] = __uint_as_float((__float_as_uint(__fsub_rn(e[i], h)) + 0x1000u) & 0xFFFFE000u);
-              }
-              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (t + (bt * kBatch + j) * kConv) * 16),
-                           "f"(e[0]), "f"(e[1]), "f"(e[2]), "f"(e[3])
-                           : "memory");
+            for (int i = 0; i < 4; ++i) {
+              const float h = __uint_as_float(__float_as_uint(e[i]) & 0xFFFFE000u);   // what the MMA sees
+              if (p.flags & 4) e[i] = __fsub_rn(e[i], h);
+              else e[i] = __uint_as_float((__float_as_uint(__fsub_rn(e[i], h)) + 0x1000u) & 0xFFFFE000u);
             }
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (t + (bt * kBatch + j) * kConv) * 16),
+                         "f"(e[0]), "f"(e[1]), "f"(e[2]), "f"(e[3])
+                         : "memory");
           }
         }
         MDB_TACC(t_work, tc0);
         const long long td = MDB_T0();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> visible to UMMA
         __syncwarp();
-        if (lane == 0) {                                               // tell the leader's MMA warp
-          if (kTiming && (p.flags & 16384)) mbar_arrive_cluster_release(&lo_full[lo.slot], leader);   // diagnostic: 28 % slower
-          else mbar_arrive_cluster(&lo_full[lo.slot], leader);
-        }
+        if (lane == 0) mbar_arrive_cluster(&lo_full[lo.slot], 0);       // tell the leader's MMA warp
         MDB_TACC(t_sig, td);
         hi.advance(kHi);
         lo.advance(kLo);
@@ -313,18 +362,23 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     const int eh = (warp - 4) >> 2;                       // which 128-column half of the accumulator
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool vec_ok = (p.ldc % 4 == 0) && (((uintptr_t)p.C & 15) == 0);
-    const bool vec8_ok = (p.ldc % 8 == 0) && (((uintptr_t)p.C & 31) == 0) && !(p.flags & 1048576);   // 1048576: A/B, 128-bit stores
-    const int num_chunks = (num_k + kChunk - 1) / kChunk;
-    long long w_full = 0, t_all = MDB_T0();
-    for (int t = first_tile; t < num_tiles; t += tile_step) {
+    const bool vec_ok = (p.ldc % 4 == 0) && (((uintptr_t)p.C & 15) == 0) &&
+                        (!p.bias || ((uintptr_t)p.bias & 15) == 0) &&
+                        (!p.mask_src || (p.ld_mask % 4 == 0 && ((uintptr_t)p.mask_src & 15) == 0));
+    const bool vec8_ok = vec_ok && (p.ldc % 8 == 0) && (((uintptr_t)p.C & 31) == 0);
+    const uint64_t pol_c = l2_policy(p.hint_c);
+    const int slot_warp = (int)rank * kPairEpiWarps + (warp - 4);          // 0..15 inside the cluster
+    long long w_full = 0, w_sk = 0, t_all = MDB_T0();
+    Segment s;
+    for (WorkIter w(p, cluster, nclusters, num_k); w.next(s);) {
       int m_blk, n_blk;
-      tile_coords(tp, t, m_blk, n_blk);
+      tile_coords_pair(p, s.tile, m_blk, n_blk);
       const int row = m_blk * 256 + (int)rank * BM + q * 32 + lane;
-      const int n0 = (n_blk * kMc + (int)pair) * 256 + eh * 128;
+      const int n0 = n_blk * 256 + eh * 128;
       float sum[128];
 #pragma unroll
       for (int j = 0; j < 128; ++j) sum[j] = 0.f;
+      const int num_chunks = (s.kb1 - s.kb0 + kChunk - 1) / kChunk;
       for (int ch = 0; ch < num_chunks; ++ch) {
         const long long tw = MDB_T0();
         mbar_wait(&tmem_full[acc], acc_phase);
@@ -341,42 +395,98 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
         }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], leader);
+        if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (row < p.M && !(kTiming && (p.flags & 524288))) {   // 524288: diagnostic, skip the C store
+      // ---- stream-K hand-over ------------------------------------------------------------------
+      if (s.kb0 > 0) {
+        // this cluster continued a tile another cluster owns: deposit the register sums, raise the flag
+        float* part = p.sk_partials + ((size_t)cluster * (2 * kPairEpiWarps) + slot_warp) * 4096;
+#pragma unroll
+        for (int j = 0; j < 128; ++j) __stcg(part + j * 32 + lane, sum[j]);
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release_gpu(p.sk_flags + cluster * (2 * kPairEpiWarps) + slot_warp, 1u);
+        continue;
+      }
+      if (s.kb1 < num_k) {
+        // owner of a tile whose k-range continues in the following clusters: add their sums in order
+        const long long tile_end = (long long)(s.tile - p.dp_tiles + 1) * num_k;
+        const long long tw = MDB_T0();
+        for (int c2 = cluster + 1; c2 < p.sk_clusters && (long long)c2 * p.sk_share < tile_end; ++c2) {
+          uint32_t* flag = p.sk_flags + c2 * (2 * kPairEpiWarps) + slot_warp;
+          if (lane == 0) {
+            long long t0 = 0;
+            for (uint32_t spins = 0; ld_acquire_gpu(flag) == 0u; ++spins) {
+              if (spins == 64) t0 = clock64();
+              if (spins > 64 && (spins & 1023) == 0 && clock64() - t0 > 4000000000ll) __trap();
+            }
+          }
+          __syncwarp();
+          const float* part = p.sk_partials + ((size_t)c2 * (2 * kPairEpiWarps) + slot_warp) * 4096;
+#pragma unroll
+          for (int j = 0; j < 128; ++j) sum[j] = __fadd_rn(sum[j], __ldcg(part + j * 32 + lane));
+          __syncwarp();
+          if (lane == 0) *(volatile uint32_t*)flag = 0u;      // slot is free for the next launch
+        }
+        MDB_TACC(w_sk, tw);
+      }
+      // ---- store (with the fused epilogue) -----------------------------------------------------
+      if (row < p.M) {
         float* crow = p.C + (int64_t)row * p.ldc;
+        const float* mrow = p.mask_src ? p.mask_src + (int64_t)row * p.ld_mask : nullptr;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int col0 = n0 + c * 32;
-          if (vec8_ok && !p.accumulate && col0 + 32 <= p.N) {
-            // 256-bit stores (sm_100): every instruction writes one whole 32-B sector of this thread's
-            // row.  With 128-bit stores each sector took two half-writes and the tile store
-            // (128 KB per CTA, all CTAs at once) outlasted the two chunks of TMEM lookahead: ~50 us
-            // of exposed store time per 128 MB of output.
+          if (vec_ok && col0 + 32 <= p.N) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8)
-              asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(crow + col0 + j),
-                           "f"(sum[c * 32 + j]), "f"(sum[c * 32 + j + 1]), "f"(sum[c * 32 + j + 2]),
-                           "f"(sum[c * 32 + j + 3]), "f"(sum[c * 32 + j + 4]), "f"(sum[c * 32 + j + 5]),
-                           "f"(sum[c * 32 + j + 6]), "f"(sum[c * 32 + j + 7])
-                           : "memory");
-          } else if (vec_ok && col0 + 32 <= p.N) {
+            for (int j = 0; j < 32; j += 8) {
+              float o[8];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 v = make_float4(sum[c * 32 + j], sum[c * 32 + j + 1], sum[c * 32 + j + 2], sum[c * 32 + j + 3]);
-              float4* dst = (float4*)(crow + col0 + j);
-              if (p.accumulate) {
-                const float4 o = *dst;
-                v = make_float4(__fadd_rn(o.x, v.x), __fadd_rn(o.y, v.y), __fadd_rn(o.z, v.z), __fadd_rn(o.w, v.w));
+              for (int i = 0; i < 8; ++i) o[i] = sum[c * 32 + j + i];
+              if (p.bias) {
+                const float4 b0 = __ldg((const float4*)(p.bias + col0 + j)), b1 = __ldg((const float4*)(p.bias + col0 + j + 4));
+                const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = __fadd_rn(o[i], b[i]);
               }
-              *dst = v;
+              if (p.relu) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = o[i] > 0.f ? o[i] : 0.f;
+              }
+              if (mrow) {
+                const float4 m0 = __ldg((const float4*)(mrow + col0 + j)), m1 = __ldg((const float4*)(mrow + col0 + j + 4));
+                const float m[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = __fmul_rn(o[i], m[i] > 0.f ? 1.f : 0.f);
+              }
+              if (p.accumulate) {
+                const float4 c0 = *(const float4*)(crow + col0 + j), c1 = *(const float4*)(crow + col0 + j + 4);
+                const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = __fadd_rn(cc[i], o[i]);
+              }
+              if (vec8_ok) {
+                // 256-bit stores (sm_100): every instruction writes one whole 32-B sector of this thread's
+                // row; with 128-bit stores each sector took two half-writes and the tile store outlasted
+                // the two chunks of TMEM lookahead
+                asm volatile("st.global.L2::cache_hint.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8}, %9;" ::"l"(crow + col0 + j),
+                             "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]),
+                             "l"(pol_c)
+                             : "memory");
+              } else {
+                *(float4*)(crow + col0 + j) = make_float4(o[0], o[1], o[2], o[3]);
+                *(float4*)(crow + col0 + j + 4) = make_float4(o[4], o[5], o[6], o[7]);
+              }
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (col0 + j < p.N) {
                 float v = sum[c * 32 + j];
+                if (p.bias) v = __fadd_rn(v, p.bias[col0 + j]);
+                if (p.relu) v = v > 0.f ? v : 0.f;
+                if (mrow) v = __fmul_rn(v, mrow[col0 + j] > 0.f ? 1.f : 0.f);
                 if (p.accumulate) v = __fadd_rn(crow[col0 + j], v);
                 crow[col0 + j] = v;
               }
@@ -386,6 +496,7 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     }
     if (kTiming && warp == 4 && lane == 0) {
       p.timing[blockIdx.x * 16 + 11] = w_full; p.timing[blockIdx.x * 16 + 12] = clock64() - t_all;
+      p.timing[blockIdx.x * 16 + 13] = w_sk;
     }
   }
 
@@ -398,4 +509,3 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
-

@@ -398,7 +398,6 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 
 
 #include "gemm_pair.cuh"      // CTA-pair kernel (the default for large problems)
-#include "gemm_pair_ts.cuh"   // experimental: A operand in tensor memory
 
 // ---- operand pre-pass: hi = rn_tf32(x), lo = rn_tf32(x - hi) into compact planes ----------------
 // The plane keeps the operand's memory order: [outer][inner] with `inner` the unit-stride axis.
@@ -507,88 +506,179 @@ static int launch(const CUtensorMap maps[4], const tc::Params& p) {
 }
 
 typedef void (*PairKernel)(const CUtensorMap, const CUtensorMap, const tc::PairParams);
+extern uint64_t g_gemm_path[MDB_GEMM_NPATHS];
 
-// shared launcher of the CTA-pair kernels; `state` caches the occupancy query per instantiation
-static int launch_pair_impl(PairKernel kern, PairKernel tkern, int smem_total, int* state, const char* tag,
-                            const CUtensorMap& map_a, const CUtensorMap& map_b, const tc::PairParams& p,
-                            int cluster_ctas = 2) {
-  int& max_clusters = *state;
+// tuning knobs (mdb_gemm_knob): -1 = automatic
+int g_knob_raster = -1, g_knob_group = -1, g_knob_hint_a = -1, g_knob_hint_b = -1, g_knob_hint_c = -1;
+int g_knob_streamk = -1;          // -1 auto, 0 never, 1 whenever the split is legal
+int g_knob_l2_budget_mb = 40;     // bytes of one operand the tile order tries to keep L2-resident
+
+constexpr int kPairHi = 4, kPairLo = 3;
+using PairSmem = tc::Smem<tc::PBN, kPairHi, kPairLo>;
+static_assert(PairSmem::TOTAL <= 227 * 1024, "shared memory budget");
+
+// one-time: opt in to the shared-memory size and ask how many CTA pairs can be co-resident
+static int pair_max_clusters(int* out) {
+  static int max_clusters = 0;
   if (!max_clusters) {
-    MDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total));
+    auto kern = tc::gemm_3xtf32_pair_kernel<kPairHi, kPairLo, false>;
+    MDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PairSmem::TOTAL));
+    MDB_CUDA(cudaFuncSetAttribute(tc::gemm_3xtf32_pair_kernel<kPairHi, kPairLo, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, PairSmem::TOTAL));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(g_sm_count / cluster_ctas * cluster_ctas, 1, 1);
+    cfg.gridDim = dim3(g_sm_count / 2 * 2, 1, 1);
     cfg.blockDim = dim3(tc::kPairThreads, 1, 1);
-    cfg.dynamicSmemBytes = smem_total;
+    cfg.dynamicSmemBytes = PairSmem::TOTAL;
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = cluster_ctas; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr; cfg.numAttrs = 1;
     int n = 0;
     if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
       cudaGetLastError();
-      n = g_sm_count / cluster_ctas;
+      n = g_sm_count / 2;
     }
-    max_clusters = std::min(n, g_sm_count / cluster_ctas);
+    max_clusters = std::min(n, g_sm_count / 2);
   }
-  const int tiles = p.tiles_m * p.tiles_n;
-  const int clusters = std::min(tiles, max_clusters);
+  *out = max_clusters;
+  return 0;
+}
+
+// stream-K workspace: one 256 x 256 fp32 slot + 16 flags per cluster.  Allocated once, outside any
+// CUDA-graph capture (a capture cannot cudaMalloc): while unavailable the planner stays data-parallel.
+static float* g_sk_partials = nullptr;
+static uint32_t* g_sk_flags = nullptr;
+static bool sk_workspace_ready() {
+  if (g_sk_partials) return true;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(g_stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return false;
+  }
+  const size_t clusters = (size_t)g_sm_count / 2;
+  void *a = nullptr, *b = nullptr;
+  if (cudaMalloc(&a, clusters * tc::kSkSlotFloats * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&b, clusters * 16 * sizeof(uint32_t)) != cudaSuccess ||
+      cudaMemsetAsync(b, 0, clusters * 16 * sizeof(uint32_t), g_stream) != cudaSuccess) {
+    cudaGetLastError();
+    if (a) cudaFree(a);
+    if (b) cudaFree(b);
+    return false;
+  }
+  g_sk_partials = (float*)a;
+  g_sk_flags = (uint32_t*)b;
+  return true;
+}
+
+// Work split + tile order + L2 hints of one CTA-pair launch.
+static void plan_pair(tc::PairParams& q, int max_clusters, int* grid_clusters, bool* streamk) {
+  const int tiles = q.tiles_m * q.tiles_n, C = max_clusters;
+  const int num_k = (q.K + tc::BK - 1) / tc::BK;
+  const double panel = 256.0 * (double)q.K * 4.0;                // one 256-row operand panel, bytes
+  const double a_total = (double)q.M * q.K * 4.0, b_total = (double)q.N * q.K * 4.0;
+  const double budget = (double)g_knob_l2_budget_mb * 1048576.0;
+  // ---- tile order: keep `group` panels of the SMALLER operand resident in L2 and stream the other
+  // one past them; when not even one panel fits (K = batch in the dW GEMMs) fall back to near-square
+  // waves whose clusters march through k together (every byte is shared inside the wave only)
+  int raster, group, hint_a = 0, hint_b = 0;
+  const int fit = (int)(budget / panel);
+  if (fit >= 1) {
+    if (b_total <= a_total) {
+      raster = 1; group = std::min(q.tiles_n, fit); hint_b = 2; hint_a = 1;
+    } else {
+      raster = 0; group = std::min(q.tiles_m, fit); hint_a = 2; hint_b = 1;
+    }
+  } else {
+    raster = 0; group = std::min(q.tiles_m, 8);
+  }
+  if (g_knob_raster >= 0) raster = g_knob_raster;
+  if (g_knob_group > 0) group = std::min(g_knob_group, raster ? q.tiles_n : q.tiles_m);
+  q.raster = raster; q.group = std::max(group, 1);
+  q.hint_a = g_knob_hint_a >= 0 ? g_knob_hint_a : hint_a;
+  q.hint_b = g_knob_hint_b >= 0 ? g_knob_hint_b : hint_b;
+  const double c_bytes = (double)q.M * q.N * 4.0;
+  q.hint_c = g_knob_hint_c >= 0 ? g_knob_hint_c : ((!q.accumulate && c_bytes > 32.0 * 1048576.0) ? 1 : 0);
+  // ---- work split
+  q.dp_tiles = tiles; q.sk_clusters = 0; q.sk_share = 0;
+  q.sk_partials = nullptr; q.sk_flags = nullptr;
+  *grid_clusters = std::min(tiles, C);
+  *streamk = false;
+  const int w = tiles / C, R = tiles % C;
+  if (R == 0 || g_knob_streamk == 0 || num_k < 2 * tc::kChunk) return;
+  const double t_dp = w + 1.0;
+  int sk_clusters = 0, share = 0;
+  double t_sk = t_dp;
+  const int s = C / R;
+  if (s >= 2) {
+    // even split: every remaining tile is cut into s equal k-ranges; the clusters of one range march
+    // through k together, so operand sharing in L2 is as good as in a data-parallel wave
+    share = ((num_k + s - 1) / s + tc::kChunk - 1) / tc::kChunk * tc::kChunk;
+    sk_clusters = (int)(((long long)R * num_k + share - 1) / share);
+    t_sk = w + (double)share / num_k + 0.02;                   // + fix-up
+  } else if (std::min(a_total + b_total, ((R + q.group - 1) / q.group + q.group) * panel) <= 80.0 * 1048576.0 ||
+             g_knob_streamk == 1) {
+    // true stream-K of the last wave: its clusters drift apart in k, which costs nothing only while
+    // the operand panels those R tiles touch stay in L2 between the drifting readers
+    const long long total = (long long)R * num_k;
+    share = (int)(((total + C - 1) / C + tc::kChunk - 1) / tc::kChunk * tc::kChunk);
+    sk_clusters = (int)((total + share - 1) / share);
+    t_sk = w + (double)share / num_k + 0.02;
+  }
+  if (sk_clusters == 0 || share < 2 * tc::kChunk) return;
+  if (g_knob_streamk != 1 && t_sk > 0.96 * t_dp) return;
+  if (!sk_workspace_ready()) return;
+  q.dp_tiles = w * C; q.sk_clusters = sk_clusters; q.sk_share = share;
+  q.sk_partials = g_sk_partials; q.sk_flags = g_sk_flags;
+  *grid_clusters = w > 0 ? C : sk_clusters;
+  *streamk = true;
+}
+
+int g_last_plan[8] = {};   // mdb_gemm_last_plan: clusters, raster, group, dp_tiles, sk_clusters, sk_share, hints, tiles
+
+static int launch_pair(const CUtensorMap& map_a, const CUtensorMap& map_b, tc::PairParams& q) {
+  int max_clusters = 0;
+  MDB_TRY(pair_max_clusters(&max_clusters));
+  int clusters = 0;
+  bool streamk = false;
+  plan_pair(q, max_clusters, &clusters, &streamk);
+  g_last_plan[0] = clusters; g_last_plan[1] = q.raster; g_last_plan[2] = q.group; g_last_plan[3] = q.dp_tiles;
+  g_last_plan[4] = q.sk_clusters; g_last_plan[5] = q.sk_share;
+  g_last_plan[6] = q.hint_a * 100 + q.hint_b * 10 + q.hint_c; g_last_plan[7] = q.tiles_m * q.tiles_n;
   static const bool timing = getenv("MDB_GEMM_TIMING") != nullptr;
   if (!timing) {
-    kern<<<cluster_ctas * clusters, tc::kPairThreads, smem_total, g_stream>>>(map_a, map_b, p);
+    tc::gemm_3xtf32_pair_kernel<kPairHi, kPairLo, false>
+        <<<2 * clusters, tc::kPairThreads, PairSmem::TOTAL, g_stream>>>(map_a, map_b, q);
     MDB_CHECK_LAUNCH();
+    ++g_gemm_path[streamk ? MDB_GEMM_PATH_TC_PAIR_STREAMK : MDB_GEMM_PATH_TC_PAIR];
     return 0;
   }
   // diagnostic mode: per-role stall cycles, averaged over leader / follower CTAs, printed to stderr
   static unsigned long long* dbuf = nullptr;
   if (!dbuf) MDB_CUDA(cudaMalloc(&dbuf, 16 * 8 * 2 * 148));
-  MDB_CUDA(cudaMemsetAsync(dbuf, 0, 16 * 8 * cluster_ctas * clusters, g_stream));
-  tc::PairParams q = p;
+  MDB_CUDA(cudaMemsetAsync(dbuf, 0, 16 * 8 * 2 * clusters, g_stream));
   q.timing = dbuf;
-  MDB_CUDA(cudaFuncSetAttribute(tkern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total));
-  tkern<<<cluster_ctas * clusters, tc::kPairThreads, smem_total, g_stream>>>(map_a, map_b, q);
+  tc::gemm_3xtf32_pair_kernel<kPairHi, kPairLo, true>
+      <<<2 * clusters, tc::kPairThreads, PairSmem::TOTAL, g_stream>>>(map_a, map_b, q);
   MDB_CHECK_LAUNCH();
-  std::vector<unsigned long long> h(16 * cluster_ctas * clusters);
+  ++g_gemm_path[streamk ? MDB_GEMM_PATH_TC_PAIR_STREAMK : MDB_GEMM_PATH_TC_PAIR];
+  std::vector<unsigned long long> h(16 * 2 * clusters);
   MDB_CUDA(cudaMemcpyAsync(h.data(), dbuf, h.size() * 8, cudaMemcpyDeviceToHost, g_stream));
   MDB_CUDA(cudaStreamSynchronize(g_stream));
-  static const char* names[13] = {"prod.wait_hi_empty", "prod.total", "mma.wait_lo_full", "mma.wait_tmem_empty", "mma.total",
+  static const char* names[14] = {"prod.wait_hi_empty", "prod.total", "mma.wait_lo_full", "mma.wait_tmem_empty", "mma.total",
                                   "-", "conv.wait_hi_full", "conv.wait_lo_empty", "conv.work", "conv.fence+arrive",
-                                  "conv.total", "epi.wait_tmem_full", "epi.total"};
-  const double kblocks = (double)((p.K + tc::BK - 1) / tc::BK) * ((tiles + clusters - 1) / clusters);
-  fprintf(stderr, "[gemm timing] %s M=%d N=%d K=%d flags=%d  (cycles per k-block, leader | follower)\n", tag, p.M,
-          p.N, p.K, p.flags);
-  for (int i = 0; i < 13; ++i) {
+                                  "conv.total", "epi.wait_tmem_full", "epi.total", "epi.wait_streamk"};
+  const int tiles = q.tiles_m * q.tiles_n;
+  const double kblocks = (double)((q.K + tc::BK - 1) / tc::BK) * tiles / clusters;
+  fprintf(stderr, "[gemm timing] pair M=%d N=%d K=%d raster=%d group=%d dp_tiles=%d sk=%dx%d  (cycles per k-block, "
+                  "leader | follower)\n", q.M, q.N, q.K, q.raster, q.group, q.dp_tiles, q.sk_clusters, q.sk_share);
+  for (int i = 0; i < 14; ++i) {
     if (i == 5) continue;
-    double s[2] = {0, 0};
-    for (int c = 0; c < cluster_ctas * clusters; ++c) s[c & 1] += (double)h[c * 16 + i];
-    const double per = (double)clusters * (cluster_ctas / 2) * kblocks;
-    fprintf(stderr, "  %-22s %9.1f | %9.1f\n", names[i], s[0] / per, s[1] / per);
+    double sacc[2] = {0, 0};
+    for (int c = 0; c < 2 * clusters; ++c) sacc[c & 1] += (double)h[c * 16 + i];
+    const double per = (double)clusters * kblocks;
+    fprintf(stderr, "  %-22s %9.1f | %9.1f\n", names[i], sacc[0] / per, sacc[1] / per);
   }
   return 0;
-}
-
-
-template <int kHi, int kLo>
-static int launch_pair(const CUtensorMap& map_a, const CUtensorMap& map_b, const tc::PairParams& p) {
-  using S = tc::Smem<tc::PBN, kHi, kLo>;
-  static_assert(S::TOTAL <= 227 * 1024, "shared memory budget");
-  static int state = 0;
-  return launch_pair_impl(tc::gemm_3xtf32_pair_kernel<kHi, kLo, false>, tc::gemm_3xtf32_pair_kernel<kHi, kLo, true>,
-                          S::TOTAL, &state, kLo == 3 ? "pair<4,3>" : "pair<5,2>", map_a, map_b, p);
-}
-template <int kHi, int kLo>
-static int launch_pair_mc(const CUtensorMap& map_a, const CUtensorMap& map_b, const tc::PairParams& p) {
-  using S = tc::Smem<tc::PBN, kHi, kLo>;
-  static int state = 0;
-  return launch_pair_impl(tc::gemm_3xtf32_pair_kernel<kHi, kLo, false, 2>, tc::gemm_3xtf32_pair_kernel<kHi, kLo, true, 2>,
-                          S::TOTAL, &state, "pair_mc<4,3>", map_a, map_b, p, 4);
-}
-template <int kRaw>
-static int launch_pair_ts(const CUtensorMap& map_a, const CUtensorMap& map_b, const tc::PairParams& p) {
-  using S = tc::SmemTs<kRaw>;
-  static_assert(S::TOTAL <= 227 * 1024, "shared memory budget");
-  static int state = 0;
-  return launch_pair_impl(tc::gemm_3xtf32_pair_ts_kernel<kRaw, false>, tc::gemm_3xtf32_pair_ts_kernel<kRaw, true>,
-                          S::TOTAL, &state, "pair_ts", map_a, map_b, p);
 }
 
 // Wave efficiency of a persistent grid: useful tile-slots / occupied tile-slots.
@@ -608,7 +698,9 @@ static bool tma_addressable(const float* ptr, int64_t s_mn, int64_t s_k, int mn,
   return *pitch % 4 == 0 && *pitch < (int64_t(1) << 36);
 }
 
-int gemm_tcgen05(const mdb_array* c, const mdb_array* a, const mdb_array* b, int accumulate) {
+// epi: optional fused epilogue (bias / relu / mask); only the CTA-pair kernel implements it, so a
+// call that carries one returns MDB_ENOTSUP when the pair kernel cannot take the problem
+int gemm_tcgen05(const mdb_array* c, const mdb_array* a, const mdb_array* b, int accumulate, const GemmEpilogue* epi) {
   const int64_t M = a->shape[0], K = a->shape[1], N = b->shape[1];
   // small problems are launch-latency bound: the CUDA-core kernel is as fast
   if (M * N * K < (int64_t(1) << 21) || K < 32 || M < 32 || N < 32)
@@ -627,6 +719,8 @@ int gemm_tcgen05(const mdb_array* c, const mdb_array* a, const mdb_array* b, int
   const bool raw = !no_raw &&
       tma_addressable((const float*)a->ptr, a->strides[0], a->strides[1], (int)M, (int)K, &a_mn, &a_pitch) &&
       tma_addressable((const float*)b->ptr, b->strides[1], b->strides[0], (int)N, (int)K, &b_mn, &b_pitch);
+  if (epi && !(raw && M > tc::BM && N > tc::PBN))
+    return set_error(MDB_ENOTSUP, "fused epilogue needs the CTA-pair kernel (M > 128, N > 128, TMA-addressable operands)");
   if (raw) {
     // TMA reads the user's arrays directly; the raw tile doubles as the hi plane
     if (!a_mn) MDB_TRY(make_map(&maps[0], (const float*)a->ptr, (int)K, (int)M, (int)a_pitch, tc::BM, false));
@@ -646,35 +740,36 @@ int gemm_tcgen05(const mdb_array* c, const mdb_array* a, const mdb_array* b, int
     MDB_TRY(make_map(&maps[3], (const float*)pb.lo.ptr, pb.inner, pb.outer, pb.ld, b_box, pb.mn_major));
     p.a_mn_major = pa.mn_major; p.b_mn_major = pb.mn_major;
   }
-  if (raw && !(g_gemm_flags & 16) && M > tc::BM && N > tc::PBN) {
+  if (raw && (!(g_gemm_flags & 16) || epi) && M > tc::BM && N > tc::PBN) {
     // CTA-pair kernel unless wave quantisation of its 256 x 256 tiles eats the gain (measured ratio
     // of the two kernels' per-flop rates: see profiles/)
     const int64_t pm = (M + 255) / 256, pn = (N + 255) / 256;
     const int64_t sm = (M + tc::BM - 1) / tc::BM, sn = (N + BN - 1) / BN;
     const double useful_pair = (double)M * N / ((double)pm * pn * 65536.0);
     const double useful_single = (double)M * N / ((double)sm * sn * 16384.0);
-    const double e_pair = wave_eff(pm * pn, g_sm_count / 2) * useful_pair * g_pair_speedup;
+    // (the pair kernel's last wave can be stream-K split, so its wave loss is at most ~1/(2C) tile)
+    int maxc = 0;
+    MDB_TRY(pair_max_clusters(&maxc));
+    const int64_t pt = pm * pn;
+    double pair_waves = (double)((pt + maxc - 1) / maxc);
+    if (g_knob_streamk != 0 && pt % maxc != 0 && K >= 2048) {
+      const int64_t R = pt % maxc, sdiv = maxc / R;
+      const double last = sdiv >= 2 ? 1.0 / (double)sdiv : 1.0;
+      pair_waves = (double)(pt / maxc) + last + 0.03;
+    }
+    const double e_pair = (double)pt / (pair_waves * maxc) * useful_pair * g_pair_speedup;
     const double e_single = wave_eff(sm * sn, g_sm_count) * useful_single;
-    if (e_pair >= e_single || (g_gemm_flags & 32)) {
-      tc::PairParams q;
+    if (e_pair >= e_single || (g_gemm_flags & 32) || epi) {
+      tc::PairParams q = {};
       q.M = (int)M; q.N = (int)N; q.K = (int)K;
       q.a_mn_major = a_mn; q.b_mn_major = b_mn;
       q.C = (float*)c->ptr; q.ldc = c->strides[0];
       q.accumulate = accumulate;
-      q.tiles_m = (int)pm; q.tiles_n = (int)pn; q.group_m = 8;
+      q.tiles_m = (int)pm; q.tiles_n = (int)pn;
       q.flags = g_gemm_flags;
       q.timing = nullptr;
-      if ((g_gemm_flags & 2097152) && pn % 2 == 0) {
-        // cluster of 4: two pairs on horizontally adjacent tiles share their A tiles by TMA multicast;
-        // a K-major A tile is fetched as two 64-row halves (one per pair), so its box is 32 x 64
-        CUtensorMap map_a_mc = maps[0];
-        if (!a_mn) MDB_TRY(make_map(&map_a_mc, (const float*)a->ptr, (int)K, (int)M, (int)a_pitch, 64, false));
-        q.tiles_n = (int)(pn / 2);
-        return launch_pair_mc<4, 3>(map_a_mc, maps[2], q);
-      }
-      if (g_gemm_flags & 131072) return launch_pair_ts<5>(maps[0], maps[2], q);   // experimental: A in TMEM
-      if (g_gemm_flags & 64) return launch_pair<5, 2>(maps[0], maps[2], q);   // A/B switches
-      return launch_pair<4, 3>(maps[0], maps[2], q);
+      if (epi) { q.bias = epi->bias; q.relu = epi->relu; q.mask_src = epi->mask_src; q.ld_mask = epi->ld_mask; }
+      return launch_pair(maps[0], maps[2], q);
     }
   }
   p.raw = raw ? 1 : 0;
@@ -687,7 +782,9 @@ int gemm_tcgen05(const mdb_array* c, const mdb_array* a, const mdb_array* b, int
   const char* dbg = getenv("MDB_GEMM_DEBUG");
   p.debug = dbg ? atoi(dbg) : 0;
   p.flags = g_gemm_flags;
-  return launch<BN, kHi, kLo>(maps, p);
+  MDB_TRY((launch<BN, kHi, kLo>(maps, p)));
+  ++g_gemm_path[raw ? MDB_GEMM_PATH_TC_SINGLE : MDB_GEMM_PATH_TC_PRESPLIT];
+  return 0;
 }
 
 }  // namespace mdb

@@ -103,6 +103,14 @@ struct ProfScope {
 };
 double algorithmic_bytes(const mdb_array* out, int n_in, const mdb_array* in);
 
+// optional fused epilogue of the CTA-pair GEMM: C = relu?(A@B + bias?) * (mask_src > 0)?
+struct GemmEpilogue {
+  const float* bias;       // [N], nullable
+  int relu;
+  const float* mask_src;   // [M, ld_mask], nullable
+  int64_t ld_mask;
+};
+
 // temp buffer from the caching allocator, returned on scope exit (stream-ordered => safe)
 struct TempBuf {
   void* ptr = nullptr;

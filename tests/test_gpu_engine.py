@@ -314,6 +314,99 @@ def test_c4_vs_oracle_wide(md):
     assert all(p.grad is not None for p in ps)
 
 
+BASELINE_DIMS = (1024, 4096, 4096, 1024)
+
+
+def _gemm_paths(reset=False):
+    import ctypes as C
+
+    from minidiff_b200.backend._lib import check, lib
+
+    counts = (C.c_uint64 * 8)()
+    check(lib.mdb_gemm_stats(counts, 1 if reset else 0))
+    return dict(simt=int(counts[0]), single=int(counts[1]), presplit=int(counts[2]), pair=int(counts[3]),
+                pair_streamk=int(counts[4]))
+
+
+def _close_rms(got, want, what):
+    """north_star tolerance for reductions / GEMMs, rtol 1e-4 / atol 1e-5, with the atol scaled by
+    the rms of the reference values (the gradients here are ~1e-5..1e-2, not ~1)."""
+    want = np.asarray(want)
+    rms = float(np.sqrt(np.mean(np.square(want.astype(np.float64)))))
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5 * rms, err_msg=what)
+
+
+_CASES = {}
+
+
+def _c4_baseline_case():
+    """oracle + float64 results of the BASELINE-dims C4 step, computed once for both engines"""
+    if "c4" not in _CASES:
+        X, Y, ps_np = orc.kink_safe_mlp_batch(2048, BASELINE_DIMS)
+        want = orc.config4_step(X, Y, ps_np)
+        truth = orc.config4_step(X.astype(np.float64), Y.astype(np.float64), [p.astype(np.float64) for p in ps_np])
+        _CASES["c4"] = (X, Y, ps_np, want, truth)
+    return _CASES["c4"]
+
+
+def _c5_baseline_case():
+    if "c5" not in _CASES:
+        X, Y, ps_np = orc.kink_safe_mlp_batch(8192, BASELINE_DIMS)
+        vs_np = [np.random.default_rng(100 + i).standard_normal(p.shape).astype(np.float32)
+                 for i, p in enumerate(ps_np)]
+        want = orc.config5_hvp(X, Y, ps_np, vs_np)
+        truth = orc.config5_hvp(X.astype(np.float64), Y.astype(np.float64), [p.astype(np.float64) for p in ps_np],
+                                [v.astype(np.float64) for v in vs_np])
+        _CASES["c5"] = (X, Y, ps_np, vs_np, want, truth)
+    return _CASES["c5"]
+
+
+def test_c4_baseline_dims_vs_oracle_on_the_pair_kernel(md):
+    """One full C4 training step at the BASELINE layer dims (1024-4096-4096-1024) on a 2048-row batch
+    against the oracle AND float64, rtol 1e-4 / atol 1e-5*rms.  Every GEMM of the step (3 forward,
+    3 dW, 2 dh) must have run on the CTA-pair tcgen05 kernel the benchmark measures."""
+    from minidiff_b200.backend._lib import check, lib
+
+    X, Y, ps_np, want, truth = _c4_baseline_case()
+    check(lib.mdb_gemm_config(2))
+    check(lib.mdb_gemm_tune(4 | 32))       # the pair kernel wherever it is legal (it is for all 8 GEMMs here)
+    _gemm_paths(reset=True)
+    try:
+        loss, grads, ps = run_c4(md, X, Y, ps_np)
+    finally:
+        check(lib.mdb_gemm_tune(4))
+        check(lib.mdb_gemm_config(0))
+    paths = _gemm_paths()
+    assert paths["pair"] + paths["pair_streamk"] == 8 and paths["simt"] == paths["single"] == paths["presplit"] == 0, paths
+    close(loss, want["loss"], rtol=1e-5)
+    for i in range(6):
+        _close_rms(grads[i], want["grads"][i], f"grad {i} vs oracle")
+        _close_rms(grads[i], truth["grads"][i], f"grad {i} vs float64")
+        _close_rms(ps[i].as_numpy(), want["params"][i], f"param {i} vs oracle")
+
+
+def test_c5_full_baseline_config_vs_oracle_and_float64(md):
+    """The FULL BASELINE config 5 (batch 8192, 1024-4096-4096-1024): first-order gradients of the
+    unreduced loss and the Hessian-vector product against the oracle and against float64, rtol 1e-4 /
+    atol 1e-5*rms; all 22 GEMMs (F-order / C-of-F-order / stride-0 operand mix of the second-order
+    graph) on the tensor-core path, none on the CUDA-core kernel."""
+    from minidiff_b200.backend._lib import check, lib
+
+    X, Y, ps_np, vs_np, want, truth = _c5_baseline_case()
+    check(lib.mdb_gemm_config(2))
+    _gemm_paths(reset=True)
+    try:
+        g1, hv = run_c5(md, X, Y, ps_np, vs_np)
+    finally:
+        check(lib.mdb_gemm_config(0))
+    paths = _gemm_paths()
+    assert paths["simt"] == 0 and sum(paths.values()) == 22, paths
+    for i in range(6):
+        _close_rms(g1[i], want["grads"][i], f"grad {i} vs oracle")
+        _close_rms(hv[i], want["hv"][i], f"hv {i} vs oracle")
+        _close_rms(hv[i], truth["hv"][i], f"hv {i} vs float64")
+
+
 def test_c4_param_update_requires_no_grad(md):
     X, Y = orc.mlp_data(8, DIMS[0], DIMS[-1])
     ps = [md.Tensor(p, allow_grad=True) for p in orc.mlp_params(DIMS)]
