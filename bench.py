@@ -8,19 +8,25 @@ Headline line (one JSON object on stdout, rank 0):
   value   = whole-job samples/s with inputs resident in HBM;   e2e = same through the public API
             with pinned HOST inputs (H2D of X,Y and D2H of the loss inside the timed region).
   roofline       = the dominant kernel class of the step (GEMM), timed live with CUDA events on the
-                   library's launch stream during the timed region.
-  cpu_baseline   = the NumPy oracle port of the same step on this box's host cores (bounded sample).
+                   library's launch stream during the timed region.  ONE tensor denominator everywhere:
+                   MEASURED_PEAKS.json bf16_tflops_sustained / 2 (all GEMM legs are timed inside
+                   multi-launch loops under the power cap); frac_of_burst uses bf16_tflops / 2.  The
+                   cuBLAS TF32 rate measured in this run is reported as a side note only.
+                   pipe_frac = 3 * frac: a 3xTF32 GEMM issues three tensor-core MACs per fp32 product.
+  cpu_baseline   = the UNMODIFIED reference (baseline/_ref, its NumPy backend) on this box's host
+                   cores, same workload, bounded number of steps; also inside fwd_bwd.c2/c3/c5.
   fwd_bwd (N=1)  = the single-GPU graph benchmarks of BASELINE.json: config 1 (README example, eager
                    vs one CUDA-graph replay, microseconds), config 2 (broadcast chain, GB/s vs HBM
                    roofline), config 3 (matmul fwd+bwd) and config 5 (Hessian-vector product), TFLOP/s
                    vs the tensor roofline; c4_reference_engine_dropin = the same C4 step run by the
-                   UNMODIFIED reference engine with only --backend switched (baseline/_ref present).
-  tensor roofline denominator = cuBLAS TF32 at 8192^3 measured in the same run (burst and sustained,
-                   the way MEASURED_PEAKS.json measures bf16); pipe_frac = 3 * frac because a 3xTF32
-                   GEMM issues three tensor-core MACs per fp32 product.
+                   UNMODIFIED reference engine with only --backend switched; c4_fused = the step
+                   written with md.linear_relu / md.linear (stateful fused ops).
+  dp_parity (N>1) = before timing, the NCCL-averaged gradients of one data-parallel backward are
+                   compared on rank 0 with a single-GPU backward over the same GLOBAL batch.
 
-`--impl reference` times the reference's CPU path (oracle port of the unmodified algorithm on
-NumPy/OpenBLAS with all host threads) on a bounded sample of the same workload.
+`--impl reference` runs the unmodified reference (baseline/_ref, NumPy backend, all host threads)
+on the same workload and full batch; `--workload c2|c3|c5` selects the other configs (used by the
+cpu_baseline legs).  Falls back to the oracle port only when baseline/_ref is absent.
 """
 from __future__ import annotations
 
@@ -51,6 +57,11 @@ C2_TRAFFIC_BYTES_PER_ITER = 3.990e9
 C2_TRAFFIC_SRC = ("dram__bytes_read.sum + dram__bytes_write.sum over the 13 launches of one iteration, "
                   "profiles/r01_c2_launches_v3.csv (below the algorithmic 4.295e9: part of each output is still "
                   "in the 126 MB L2 when the next op reads it)")
+GEMM_TRAFFIC_SRC = ("dram__bytes_read.sum + dram__bytes_write.sum averaged over the 8 GEMM launches of one C4 step "
+                    "(ncu --set full, profiles/r02_ncu_mlp_step_gemm.md)")
+C3_TRAFFIC_BYTES_PER_LAUNCH = 2.65e9
+C3_TRAFFIC_SRC = ("dram__bytes_read.sum + dram__bytes_write.sum per 8192^3 launch of the shipped pair kernel "
+                  "(ncu --set full, profiles/r02_ncu_c3_gemm.md)")
 GLOBAL_BATCH = 65536
 DIMS = (1024, 4096, 4096, 1024)
 LR = 0.01
@@ -64,6 +75,23 @@ def load_peaks():
         return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"],
                 "bf16_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
     return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "src": "fallback"}
+
+
+def tensor_roofline(tflops, peaks, **extra):
+    """ONE denominator for every GEMM leg: MEASURED_PEAKS.json bf16_tflops_sustained / 2 (the legs
+    are timed inside multi-launch loops, i.e. under the power cap); the burst figure and the cuBLAS
+    TF32 rate measured in this run are side notes.  pipe_frac = 3 * frac (3xTF32 issues three
+    tensor-core MACs per fp32 product)."""
+    peak, burst = peaks["bf16_sustained"] / 2.0, peaks["bf16_burst"] / 2.0
+    r = {"bound": "tensor", "achieved": tflops, "peak": peak, "unit": "TFLOP/s",
+         "frac": tflops / peak, "pipe_frac": 3.0 * tflops / peak, "frac_of_burst": tflops / burst,
+         "peak_src": f"{peaks['src']} bf16_tflops_sustained / 2 (MEASURED_PEAKS.json: dense bf16 cuBLAS, "
+                     "sustained under the power cap; TF32 runs at half the bf16 rate)",
+         "note": "achieved = algorithmic 2MNK flops / CUDA-event time of the GEMM launches inside the timed "
+                 "region; a 3xTF32 GEMM issues 3 tensor-core MACs per fp32 product, so the tensor pipe does "
+                 "pipe_frac = 3*frac of the yardstick's work"}
+    r.update(extra)
+    return r
 
 
 def measure_tf32_peak(seconds=2.0, n=8192):
@@ -214,6 +242,12 @@ class Dev:
         return {"in_use_GB": v[0].value / 1e9, "cached_GB": v[1].value / 1e9, "peak_GB": v[2].value / 1e9,
                 "device_allocs": v[3].value}
 
+    def gemm_paths(self, reset=False):
+        c = (self.C.c_uint64 * 8)()
+        self.check(self.lib.mdb_gemm_stats(c, 1 if reset else 0))
+        return {"simt": int(c[0]), "tc_single": int(c[1]), "tc_presplit": int(c[2]), "tc_pair": int(c[3]),
+                "tc_pair_streamk": int(c[4])}
+
     def prof(self, on):
         self.check(self.lib.mdb_prof_enable(1 if on else 0))
 
@@ -299,6 +333,7 @@ def bench_mlp(dev, dist, rank, world, steps, warmup, peaks):
     params = [md.Tensor(p, allow_grad=True) for p in W.mlp_params(DIMS)]
     X, Y = md.Tensor(X_np), md.Tensor(Y_np)
     dp = DataParallel(params, rank, world) if world > 1 else None
+    dp_parity = dp_parity_check(dev, dist, rank, world, dp, X, Y, params, local) if world > 1 else None
 
     def step():
         return W.mlp_train_step(X, Y, params, LR, dp)
@@ -317,6 +352,7 @@ def bench_mlp(dev, dist, rank, world, steps, warmup, peaks):
     sampler.mark_begin()
     l0 = dev.launches()
     allocs0 = dev.mem()["device_allocs"]
+    dev.gemm_paths(reset=True)
     dev.record(e0)
     for _ in range(steps):
         loss = step()
@@ -333,6 +369,7 @@ def bench_mlp(dev, dist, rank, world, steps, warmup, peaks):
     ew_ms, ew_n, ew_bytes = dev.prof_read(0)
     red_ms, red_n, red_bytes = dev.prof_read(1)
     dev.prof(False)
+    gemm_paths = dev.gemm_paths()
     rank_ms = all_ranks(dist, ms / steps)
     ms = max_over_ranks(dist, ms)
     loss_value = float(loss.item())
@@ -360,7 +397,6 @@ def bench_mlp(dev, dist, rank, world, steps, warmup, peaks):
     if dp is not None:
         dp.close()
 
-    tf32_peak = peaks["tf32_sustained"]
     gemm_tflops = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     out = {
         "metric": METRIC, "value": GLOBAL_BATCH * steps / (ms * 1e-3), "unit": "samples/s",
@@ -379,24 +415,15 @@ def bench_mlp(dev, dist, rank, world, steps, warmup, peaks):
         "gpu_launches": launches,
         "memory": mem,
         "clocks": clocks,
-        "roofline": {
-            "bound": "tensor", "kernel": "mdb_gemm (matmul fwd + dW/dX gradient GEMMs)",
-            "achieved": gemm_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
-            "frac": gemm_tflops / tf32_peak if tf32_peak else None,
-            "pipe_frac": 3.0 * gemm_tflops / tf32_peak if tf32_peak else None,
-            "traffic": GEMM_TRAFFIC_BYTES_PER_LAUNCH if world == 1 else None,
-            "traffic_src": "dram__bytes_read.sum + dram__bytes_write.sum averaged over the 8 GEMM launches of one "
-                           "C4 step, profiles/r01_ncu_mlp_step_gemm_pair.md (same capture: tensor pipe 83-94 % "
-                           "active at the power-capped 1.55-1.68 GHz)",
-            "algorithmic_bytes_per_launch": GEMM_ALGORITHMIC_BYTES_PER_LAUNCH if world == 1 else None,
-            "launches": int(gemm_n), "avg_launch_ms": gemm_ms / gemm_n if gemm_n else None,
-            "share_of_step": gemm_ms / ms if ms else None,
-            "note": "achieved = algorithmic 2MNK flops / CUDA-event time of the GEMM launches inside "
-                    "the timed region; peak = sustained TF32 dense rate, "
-                    f"{peaks['tf32_src']}; a 3xTF32 "
-                    "GEMM issues 3 tensor-core MACs per fp32 product, so pipe_frac = 3*frac (above 1.0 = more "
-                    "tensor work per second than the cuBLAS yardstick sustains under the same power cap)",
-        },
+        "samples_per_s_per_sm_mhz": (GLOBAL_BATCH * steps / (ms * 1e-3)) / clocks["sm_mhz"] if clocks.get("sm_mhz") else None,
+        "dp_parity": dp_parity,
+        "roofline": tensor_roofline(
+            gemm_tflops, peaks, kernel="mdb_gemm (matmul fwd + dW/dX gradient GEMMs): tc::gemm_3xtf32_pair_kernel",
+            traffic=GEMM_TRAFFIC_BYTES_PER_LAUNCH if world == 1 else None,
+            traffic_src=GEMM_TRAFFIC_SRC,
+            algorithmic_bytes_per_launch=GEMM_ALGORITHMIC_BYTES_PER_LAUNCH if world == 1 else None,
+            launches=int(gemm_n), avg_launch_ms=gemm_ms / gemm_n if gemm_n else None,
+            share_of_step=gemm_ms / ms if ms else None, gemm_paths=gemm_paths),
         "other_kernels": {
             "elementwise": {"ms_per_step": ew_ms / steps, "calls_per_step": ew_n / steps,
                             "algorithmic_GBps": ew_bytes / (ew_ms * 1e-3) / 1e9 if ew_ms else None,
@@ -406,6 +433,51 @@ def bench_mlp(dev, dist, rank, world, steps, warmup, peaks):
                        "frac_of_hbm": red_bytes / (red_ms * 1e-3) / 1e9 / peaks["hbm_gbs"] if red_ms else None},
         },
     }
+    return out
+
+
+def dp_parity_check(dev, dist, rank, world, dp, X, Y, params, local):
+    """Evidence that the data-parallel path computes the right thing on hardware (the 1-GPU test
+    lease cannot): ONE backward over the sharded global batch with the NCCL exchange, then rank 0
+    alone recomputes the gradient of the same GLOBAL batch (all ranks' shards regenerated from their
+    seeds) on its single GPU and compares.  max_rel = max over parameters of max|dp - single| /
+    max|single|; summation order differs (per-shard means averaged by NCCL), so ~1e-6 is expected."""
+    md = dev.md
+    from minidiff_b200 import workloads as W
+
+    loss = md.mean((W.mlp_forward(X, params) - Y) ** 2)
+    loss.backward()
+    dp.finish()
+    dev.sync()
+    dp_grads = [p.grad.as_numpy() for p in params]
+    dp_loss = float(loss.item())
+    losses = all_ranks(dist, dp_loss)
+    for p in params:
+        p.grad = None
+    barrier(dist)
+    out = None
+    if rank == 0:
+        shards = [W.mlp_data(local, DIMS[0], DIMS[-1], seed=1000 + 2 * r) for r in range(world)]
+        Xg = md.Tensor(np.concatenate([s[0] for s in shards]))
+        Yg = md.Tensor(np.concatenate([s[1] for s in shards]))
+        del shards
+        solo = [md.Tensor(p, allow_grad=True) for p in W.mlp_params(DIMS)]      # no grad hooks: no NCCL
+        l1 = md.mean((W.mlp_forward(Xg, solo) - Yg) ** 2)
+        l1.backward()
+        worst, worst_rms = 0.0, 0.0
+        for g, q in zip(dp_grads, solo):
+            ref = q.grad.as_numpy().astype(np.float64)
+            d = np.abs(g.astype(np.float64) - ref)
+            worst = max(worst, float(d.max() / np.abs(ref).max()))
+            worst_rms = max(worst_rms, float(np.sqrt((d ** 2).mean()) / np.sqrt((ref ** 2).mean())))
+        single_loss = float(l1.item())
+        out = {"max_rel": worst, "rms_rel": worst_rms, "ok": bool(worst < 1e-4),
+               "loss_single_gpu": single_loss, "loss_mean_over_ranks": float(np.mean(losses)),
+               "loss_rel_diff": abs(float(np.mean(losses)) - single_loss) / abs(single_loss),
+               "what": f"averaged gradients of one DP backward (world {world}, {local} rows per rank) vs a "
+                       f"single-GPU backward over the same {local * world}-row global batch on rank 0"}
+        del Xg, Yg, solo, l1
+    barrier(dist)
     return out
 
 
@@ -475,16 +547,12 @@ def bench_c3(dev, steps, warmup, peaks, n=8192):
     ms = dev.elapsed_ms(e0, e1) / steps
     g_ms, g_n, g_fl = dev.prof_read(2)
     dev.prof(False)
-    tf32_peak = peaks["tf32_burst"]
     tf = g_fl / (g_ms * 1e-3) / 1e12
     return {"workload": f"C3 C=A@B; C.backward() {n}^3 fp32 (NN fwd, NT dA, TN dB)",
             "ms_per_iter": ms, "TFLOPs_fp32_equiv": W.c3_flops(n) / (ms * 1e-3) / 1e12,
-            "roofline": {"bound": "tensor", "achieved": tf, "peak": tf32_peak, "unit": "TFLOP/s",
-                         "frac": tf / tf32_peak, "pipe_frac": 3.0 * tf / tf32_peak,
-                         "traffic": 2.65e9, "traffic_src": "profiles/r01_ncu_c3_gemm_pair_before_arrive_fix.md "
-                         "(DRAM read+write per 8192^3 launch; algorithmic 0.805e9)",
-                         "avg_launch_ms": g_ms / g_n,
-                         "note": "peak = burst TF32 dense rate (" + peaks["tf32_src"] + "); 3xTF32 pipe use = 3*frac"}}
+            "gemm_paths": dev.gemm_paths(),
+            "roofline": tensor_roofline(tf, peaks, traffic=C3_TRAFFIC_BYTES_PER_LAUNCH, traffic_src=C3_TRAFFIC_SRC,
+                                        algorithmic_bytes_per_launch=3.0 * 4.0 * n * n, avg_launch_ms=g_ms / g_n)}
 
 
 def bench_c1(dev, iters=200):
@@ -617,7 +685,6 @@ def bench_c5(dev, steps, warmup, peaks, batch=8192):
     ms = dev.elapsed_ms(e0, e1) / steps
     g_ms, g_n, g_fl = dev.prof_read(2)
     dev.prof(False)
-    tf32_peak = peaks["tf32_burst"]
     tf = g_fl / (g_ms * 1e-3) / 1e12
     return {"workload": f"C5 Hessian-vector product, same MLP, batch {batch}, allow_higher_order backward "
                         "then backward of sum(grad*v)",
@@ -625,17 +692,62 @@ def bench_c5(dev, steps, warmup, peaks, batch=8192):
             "gemm_launches_per_iter": g_n / steps, "gemm_flops_per_iter": g_fl / steps,
             "device_allocs_in_timed_region": dev.mem()["device_allocs"] - allocs0,
             "hv_norm": float(md.sum(hv[0] * hv[0]).item()) ** 0.5,
-            "roofline": {"bound": "tensor", "achieved": tf, "peak": tf32_peak, "unit": "TFLOP/s",
-                         "frac": tf / tf32_peak, "pipe_frac": 3.0 * tf / tf32_peak, "traffic": None,
-                         "gemm_share_of_iter": (g_ms / steps) / ms}}
+            "gemm_paths": dev.gemm_paths(),
+            "roofline": tensor_roofline(tf, peaks, traffic=None, gemm_share_of_iter=(g_ms / steps) / ms)}
+
+
+def bench_c4_fused(dev, steps, warmup, peaks):
+    """The C4 training step written with the stateful fused ops: md.linear_relu(X, W, b)
+    = one tcgen05 GEMM with bias + ReLU in its epilogue, md.linear for the output layer; backward
+    masks the upstream gradient once per layer (or inside the dX GEMM epilogue of the layer above)."""
+    md = dev.md
+    from minidiff_b200 import workloads as W
+
+    X_np, Y_np = W.mlp_data(GLOBAL_BATCH, DIMS[0], DIMS[-1], seed=1000)
+    params = [md.Tensor(p, allow_grad=True) for p in W.mlp_params(DIMS)]
+    X, Y = md.Tensor(X_np), md.Tensor(Y_np)
+    del X_np, Y_np
+
+    def step():
+        h = md.linear_relu(X, params[0], params[1])
+        h = md.linear_relu(h, params[2], params[3])
+        loss = md.mean((md.linear(h, params[4], params[5]) - Y) ** 2)
+        loss.backward()
+        with md.no_grad():
+            for p in params:
+                p -= LR * p.grad
+        return loss
+
+    loss = warm_until_stable(dev, step, warmup)
+    e0, e1 = dev.event(), dev.event()
+    dev.prof(True)
+    dev.gemm_paths(reset=True)
+    l0 = dev.launches()
+    dev.record(e0)
+    for _ in range(steps):
+        loss = step()
+    dev.record(e1)
+    dev.sync()
+    ms = dev.elapsed_ms(e0, e1) / steps
+    g_ms, g_n, g_fl = dev.prof_read(2)
+    ew_ms, ew_n, ew_b = dev.prof_read(0)
+    red_ms, red_n, red_b = dev.prof_read(1)
+    dev.prof(False)
+    tf = g_fl / (g_ms * 1e-3) / 1e12
+    return {"workload": "C4 training step written with md.linear_relu / md.linear (fused stateful ops)",
+            "ms_per_step": ms, "samples_per_s": GLOBAL_BATCH / (ms * 1e-3),
+            "launches_per_step": (dev.launches() - l0) / steps, "loss": float(loss.item()),
+            "gemm_paths": dev.gemm_paths(),
+            "elementwise_ms_per_step": ew_ms / steps, "reduce_ms_per_step": red_ms / steps,
+            "roofline": tensor_roofline(tf, peaks, launches=int(g_n), share_of_step=(g_ms / steps) / ms)}
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arms (oracle port == the reference's algorithm on NumPy/OpenBLAS)
+# CPU arm: the UNMODIFIED reference (baseline/_ref) on its NumPy backend, all host threads
 # ------------------------------------------------------------------------------------------------
 def use_all_host_threads():
     """torchrun exports OMP_NUM_THREADS=1, which would pin OpenBLAS (the reference's matmul) to one
-    thread; the CPU arms are meant to use every host core.  Returns the thread count in effect."""
+    thread; the CPU arm is meant to use every host core.  Returns the thread count in effect."""
     n = os.cpu_count() or 1
     try:
         from threadpoolctl import threadpool_info, threadpool_limits
@@ -647,57 +759,242 @@ def use_all_host_threads():
         return int(os.environ.get("OMP_NUM_THREADS", n))
 
 
-def cpu_mlp_samples_per_s(sample_batch, reps):
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import np_minidiff as orc
+# synthetic inputs of the BASELINE configs (pure NumPy; identical to minidiff_b200/workloads.py, repeated
+# here so that the reference arm imports nothing of this repo's engine)
+def gen_c2_inputs(n=8192, m=8192, seed=1234):
+    rng = np.random.default_rng(seed)
+    return (rng.standard_normal((n, 1)).astype(np.float32), rng.standard_normal((1, m)).astype(np.float32))
 
-    use_all_host_threads()
 
-    X, Y = orc.mlp_data(sample_batch, DIMS[0], DIMS[-1])
-    ps = orc.mlp_params(DIMS)
-    orc.config4_step(X[:256], Y[:256], ps)          # warm-up (page faults, thread pool)
-    best = None
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        orc.config4_step(X, Y, ps)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return sample_batch / best, best
+def gen_c3_inputs(n=8192):
+    return (np.random.default_rng(1234).standard_normal((n, n), dtype=np.float32),
+            np.random.default_rng(1235).standard_normal((n, n), dtype=np.float32))
+
+
+def gen_mlp_params(dims=DIMS, seed0=2):
+    ps, sd = [], seed0
+    for fi, fo in zip(dims[:-1], dims[1:]):
+        ps.append((np.random.default_rng(sd).standard_normal((fi, fo)) / np.sqrt(fi)).astype(np.float32))
+        ps.append((np.random.default_rng(sd + 1).standard_normal((fo,)) / np.sqrt(fo)).astype(np.float32))
+        sd += 2
+    return ps
+
+
+def gen_mlp_data(batch, d_in, d_out, seed=0):
+    return (np.random.default_rng(seed).standard_normal((batch, d_in), dtype=np.float32),
+            np.random.default_rng(seed + 1).standard_normal((batch, d_out), dtype=np.float32))
+
+
+def import_reference_numpy():
+    """The unmodified reference package from baseline/_ref (offline pip install of /root/reference
+    done by __graft_entry__.build(); shipped to the GPU box) on ITS OWN NumPy backend: argv is trimmed
+    because the reference parses sys.argv at import (backend/__init__.py:13-16), graphviz is stubbed
+    (only utils.py drawing uses it).  None if the install is absent."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "minidiff")):
+        return None
+    for p_ in (os.path.join(ROOT, "oracle", "_stubs"), ref_dir):
+        if p_ not in sys.path:
+            sys.path.insert(0, p_)
+    saved = sys.argv
+    sys.argv = [saved[0]]
+    try:
+        import minidiff as ref
+    finally:
+        sys.argv = saved
+    import minidiff.backend as live
+
+    if live.tensor_class is not np.ndarray:
+        raise RuntimeError("the reference did not select its NumPy backend")
+    return ref
+
+
+class PortEngine:
+    """fallback when baseline/_ref is absent: the oracle port of the same algorithm (kind 'port')"""
+
+    def __init__(self):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import np_minidiff as orc
+
+        self.orc = orc
+
+
+def ref_workload(ref, name, rows=None):
+    """(step function, units per step, unit, description) of BASELINE config `name` written against
+    the reference's public API -- the same user code as minidiff_b200/workloads.py."""
+    c2_inputs, c3_inputs, mlp_data, mlp_params = gen_c2_inputs, gen_c3_inputs, gen_mlp_data, gen_mlp_params
+    if name == "c4":
+        B = rows or GLOBAL_BATCH
+        X_np, Y_np = mlp_data(B, DIMS[0], DIMS[-1], seed=1000)
+        params = [ref.Tensor(p_, allow_grad=True) for p_ in mlp_params(DIMS)]
+        X, Y = ref.Tensor(X_np), ref.Tensor(Y_np)
+
+        def step():
+            h = X
+            for l in range(3):
+                h = h @ params[2 * l] + params[2 * l + 1]
+                if l < 2:
+                    h = ref.where(h > 0, h, 0)
+            loss = ref.mean((h - Y) ** 2)
+            loss.backward()
+            with ref.no_grad():
+                for p_ in params:
+                    p_ -= LR * p_.grad
+            return loss
+
+        return step, B, "samples/s", f"one full C4 training step on {B} rows"
+    if name == "c2":
+        a_np, c_np = c2_inputs()
+        a, c = ref.Tensor(a_np, allow_grad=True), ref.Tensor(c_np, allow_grad=True)
+
+        def step():
+            loss = ref.sum(ref.sin(a * c + a) ** 2)
+            loss.backward()
+            return loss
+
+        return step, 26.0 * (1 << 26) * 4 / 1e9, "GB/s", "one C2 iteration (26E reference-chain bytes)"
+    if name == "c3":
+        A_np, B_np = c3_inputs(8192)
+        A, Bm = ref.Tensor(A_np, allow_grad=True), ref.Tensor(B_np, allow_grad=True)
+
+        def step():
+            Cm = A @ Bm
+            Cm.backward()
+            return Cm
+
+        return step, 3 * 2.0 * 8192 ** 3 / 1e12, "TFLOP/s", "one C3 iteration (8192^3 fwd + 2 gradient GEMMs)"
+    if name == "c5":
+        B = rows or 8192
+        X_np, Y_np = mlp_data(B, DIMS[0], DIMS[-1], seed=40)
+        params = [ref.Tensor(p_, allow_grad=True) for p_ in mlp_params(DIMS)]
+        vs = [ref.Tensor(np.random.default_rng(50 + i).standard_normal(p_.shape).astype(np.float32))
+              for i, p_ in enumerate(params)]
+        X, Y = ref.Tensor(X_np), ref.Tensor(Y_np)
+
+        def step():
+            h = X
+            for l in range(3):
+                h = h @ params[2 * l] + params[2 * l + 1]
+                if l < 2:
+                    h = ref.where(h > 0, h, 0)
+            L = ((h - Y) ** 2) / float(h.size)
+            L.backward(allow_higher_order=True)
+            s_ = None
+            for p_, v in zip(params, vs):
+                t = ref.sum(p_.grad * v)
+                s_ = t if s_ is None else s_ + t
+            s_.backward()
+            return s_
+
+        flops = 2.0 * B * (71303168 + 134217728)
+        return step, flops / 1e12, "TFLOP/s", f"one C5 Hessian-vector product, batch {B} (22 GEMMs)"
+    raise ValueError(name)
 
 
 def reference_arm(args, rank):
+    """`--impl reference`: the reference's own CPU implementation of the workload, timed on this box's
+    host cores.  Rank 0 only.  C4 runs the FULL 65536-row batch per step (same config as the B200
+    arm); only if one step is so slow that K+W steps would not end within --cpu-budget-s is the
+    per-step sample reduced (and the line says so)."""
     if rank != 0:
         return
     cores = use_all_host_threads()
-    sample = 8192
+    ref = import_reference_numpy()
+    kind, src = "reference", "unmodified reference from baseline/_ref on its NumPy backend"
+    if ref is None:
+        return port_arm(args, cores)
+    name = args.workload
+    rows = args.sample_rows or None
+    step, units, unit, what = ref_workload(ref, name, rows)
+    t0 = time.perf_counter()
+    step()                                              # first warm-up step, also the cost probe
+    first = time.perf_counter() - t0
+    todo = args.warmup - 1 + args.steps
+    if name in ("c4", "c5") and rows is None and first * todo > args.cpu_budget_s:
+        full = GLOBAL_BATCH if name == "c4" else 8192
+        rows = max(2048, int(full * args.cpu_budget_s / (first * todo)) // 2048 * 2048)
+        del step
+        step, units, unit, what = ref_workload(ref, name, rows)
+        step()
+    for _ in range(max(args.warmup - 1, 0)):
+        step()
     times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        out = step()
+        times.append(time.perf_counter() - t0)
+    total = sum(times)
+    v = units * len(times) / total
+    full_cfg = (name != "c4" or rows in (None, GLOBAL_BATCH)) and (name != "c5" or rows in (None, 8192))
+    line = {
+        "impl": "reference", "metric": METRIC if name == "c4" else f"{name}_cpu_reference", "value": v, "unit": unit,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / len(times) * 1e3,
+        "best_ms_per_step": min(times) * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C4 MLP 1024-4096-4096-1024 where-ReLU mean-MSE SGD full training step" if name == "c4" else what,
+                   "global_batch": GLOBAL_BATCH if name == "c4" else None,
+                   "rows_per_step": rows or (GLOBAL_BATCH if name == "c4" else None),
+                   "full_batch": full_cfg, "parallelism": "cpu"},
+        "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": kind,
+                         "sample": f"{what}; {len(times)} timed steps after {args.warmup} warm-up; {src} "
+                                   f"(NumPy {np.__version__} / OpenBLAS: matmul on all {cores} host threads, "
+                                   "elementwise + reductions single-threaded as NumPy runs them)"},
+        "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "result_check": float(np.asarray(out.as_numpy() if hasattr(out, "as_numpy") else out).ravel()[0]),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def port_arm(args, cores):
+    """baseline/_ref missing: time the oracle port (same algorithm on NumPy) instead, C4 only."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import np_minidiff as orc
 
-    X, Y = orc.mlp_data(sample, DIMS[0], DIMS[-1])
+    rows = args.sample_rows or 8192
+    X, Y = orc.mlp_data(rows, DIMS[0], DIMS[-1])
     ps = orc.mlp_params(DIMS)
+    times = []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
         orc.config4_step(X, Y, ps)
         if i >= args.warmup:
             times.append(time.perf_counter() - t0)
-    total = sum(times)
-    v = sample * len(times) / total
-    line = {
+    v = rows * len(times) / sum(times)
+    print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / len(times) * 1e3,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sum(times) / len(times) * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "C4 MLP 1024-4096-4096-1024 where-ReLU mean-MSE SGD full training step",
-                   "global_batch": GLOBAL_BATCH, "parallelism": "cpu"},
+                   "global_batch": GLOBAL_BATCH, "rows_per_step": rows, "full_batch": rows == GLOBAL_BATCH,
+                   "parallelism": "cpu"},
         "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": f"each step = one full training step on a {sample}-row sample of the "
-                                   f"{GLOBAL_BATCH}-row batch (NumPy {np.__version__} / OpenBLAS, all host "
-                                   "threads for matmul; elementwise + reductions are single-threaded in NumPy)"},
+                         "sample": f"baseline/_ref absent: oracle port, one training step on {rows} rows"},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    print(json.dumps(line), flush=True)
+        "gpu_launches": 0}), flush=True)
+
+
+def cpu_baseline_leg(workload, steps=2, warmup=1, timeout=600):
+    """Run `bench.py --impl reference --workload X` in a SUBPROCESS (this process has already bound the
+    reference package to the B200 plugin for the drop-in leg; one backend per process) and return its
+    cpu_baseline object."""
+    env = dict(os.environ)
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        env.pop(k, None)
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", workload,
+           "--steps", str(steps), "--warmup", str(warmup)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                d = json.loads(ln)
+                cb = d["cpu_baseline"]
+                cb["ms_per_step"] = d["ms_per_step"]
+                cb["full_batch"] = d["config"].get("full_batch")
+                return cb
+        return {"error": (r.stderr or r.stdout)[-400:]}
+    except Exception as exc:
+        return {"error": repr(exc)}
 
 
 def main():
@@ -706,8 +1003,13 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--skip-extras", action="store_true", help="skip the C2/C3 single-GPU benchmarks")
-    ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="c4", choices=["c2", "c3", "c4", "c5"],
+                    help="--impl reference only: which BASELINE config the CPU reference runs")
+    ap.add_argument("--sample-rows", type=int, default=0, help="--impl reference: rows per step (0 = full batch)")
+    ap.add_argument("--cpu-budget-s", type=float, default=900.0,
+                    help="--impl reference: shrink the per-step sample if K+W full-batch steps would exceed this")
+    ap.add_argument("--skip-extras", action="store_true", help="skip the C1/C2/C3/C5 single-GPU benchmarks")
+    ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -718,42 +1020,30 @@ def main():
             sys.exit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
     warmup = max(args.warmup, 3)
     peaks = load_peaks()
-    peaks["tf32_burst"], peaks["tf32_sustained"] = peaks["bf16_burst"] / 2.0, peaks["bf16_sustained"] / 2.0
-    peaks["tf32_src"] = f"half the {peaks['src']} bf16 rate (MEASURED_PEAKS.json)"
     sys.argv = sys.argv[:1]
     dev = Dev()
     dist = dist_setup(world)
     line = bench_mlp(dev, dist, rank, world, args.steps, warmup, peaks)
-    if world == 1 and not args.skip_extras:
-        # the yardstick is taken AFTER the headline loop (2 s of cuBLAS at the power cap would
-        # pre-heat the chip for it) and the roofline of the line is re-based on it
-        m = measure_tf32_peak()
-        if m and "burst" in m:
-            peaks["tf32_burst"], peaks["tf32_sustained"] = m["burst"], m["sustained"]
-            peaks["tf32_src"] = "measured in this run: " + m["how"]
-            r = line["roofline"]
-            r["peak"] = m["sustained"]
-            r["frac"] = r["achieved"] / m["sustained"]
-            r["pipe_frac"] = 3.0 * r["frac"]
-            r["note"] = r["note"].replace("half the measured bf16 rate (MEASURED_PEAKS.json)", peaks["tf32_src"]) \
-                                 .replace("half the fallback bf16 rate (MEASURED_PEAKS.json)", peaks["tf32_src"])
-        line["roofline"]["tf32_peak_measurement"] = m
-        time.sleep(1.0)
     line["warmup"] = warmup
     if rank == 0 and world == 1:
         if not args.skip_extras:
+            # cuBLAS TF32 on this box, a SIDE NOTE (taken after the headline loop so it cannot pre-heat it);
+            # every frac in this file uses MEASURED_PEAKS.json (tensor_roofline)
+            line["roofline"]["tf32_cublas_side_note"] = measure_tf32_peak()
+            time.sleep(1.0)
             line["fwd_bwd"] = {"c1_readme": bench_c1(dev),
                                "c2_broadcast_chain": bench_c2(dev, max(args.steps, 10), warmup, peaks),
                                "c3_matmul": bench_c3(dev, max(2, min(args.steps, 5)), warmup, peaks),
                                "c5_hvp": bench_c5(dev, max(args.steps, 10), warmup, peaks),
+                               "c4_fused": bench_c4_fused(dev, max(5, min(args.steps, 10)), warmup, peaks),
                                "c4_reference_engine_dropin": bench_c4_reference_engine(dev, 5, warmup)}
         if not args.skip_cpu:
-            v, secs = cpu_mlp_samples_per_s(16384, 3)
-            line["cpu_baseline"] = {
-                "value": v, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
-                "sample": f"one full training step on a 16384-row sample of the batch, best of 3 "
-                          f"({secs:.2f} s each); NumPy {np.__version__}/OpenBLAS, matmul on all host "
-                          "threads, elementwise single-threaded"}
+            # the unmodified reference on its NumPy backend, on this box's host cores, same workloads
+            dev.md.backend.functions.synchronize()
+            line["cpu_baseline"] = cpu_baseline_leg("c4")
+            if not args.skip_extras:
+                for key, wl in (("c2_broadcast_chain", "c2"), ("c3_matmul", "c3"), ("c5_hvp", "c5")):
+                    line["fwd_bwd"][key]["cpu_baseline"] = cpu_baseline_leg(wl)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:

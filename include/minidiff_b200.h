@@ -60,6 +60,7 @@ typedef enum {
   MDB_OP_SIN, MDB_OP_COS, MDB_OP_TAN, MDB_OP_SINH, MDB_OP_COSH, MDB_OP_TANH,
   MDB_OP_EXP, MDB_OP_LOG, MDB_OP_SQRT, MDB_OP_RECIP, MDB_OP_SQUARE, MDB_OP_LOGICAL_NOT,
   MDB_OP_INVERT, MDB_OP_ISNAN,
+  MDB_OP_RELU,       /* where(x > 0, x, 0) in one pass: the forward of a user-level fused relu op */
   /* binary */
   MDB_OP_ADD = 32, MDB_OP_SUB, MDB_OP_MUL, MDB_OP_DIV, MDB_OP_POW, MDB_OP_MOD, MDB_OP_FLOORDIV,
   MDB_OP_MAXIMUM, MDB_OP_MINIMUM,

@@ -16,5 +16,11 @@ from .ops.wrapping import *  # noqa: F401,F403,E402
 from .ops.definitions import *  # noqa: F401,F403,E402
 from .caching import reuse_graph  # noqa: F401,E402
 from .graphs import CapturedGraph, capture_graph  # noqa: F401,E402
+from .ops.fused_ops import make_ops as _make_fused_ops  # noqa: E402
+
+import sys as _sys  # noqa: E402
+
+# user-level fused device ops on the stateful-op protocol: extensions, not reference names
+relu, linear_relu, linear = _make_fused_ops(_sys.modules[__name__])
 
 __version__ = "0.1.0"

@@ -43,7 +43,7 @@ BOOL, U8, I8, I16, I32, I64, F32, F64, U16, U32, U64, F16 = range(12)
 # elementwise op ids (mdb_op)
 OP = dict(
     COPY=0, NEG=1, ABS=2, SIGN=3, CEIL=4, FLOOR=5, SIN=6, COS=7, TAN=8, SINH=9, COSH=10, TANH=11,
-    EXP=12, LOG=13, SQRT=14, RECIP=15, SQUARE=16, LOGICAL_NOT=17, INVERT=18, ISNAN=19,
+    EXP=12, LOG=13, SQRT=14, RECIP=15, SQUARE=16, LOGICAL_NOT=17, INVERT=18, ISNAN=19, RELU=20,
     ADD=32, SUB=33, MUL=34, DIV=35, POW=36, MOD=37, FLOORDIV=38, MAXIMUM=39, MINIMUM=40,
     EQ=41, NE=42, GT=43, GE=44, LT=45, LE=46, AND=47, OR=48, XOR=49,
     WHERE=64, CLIP=65, FMA=66,

@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(256) ew_generic(const GenParams p) {
   X(MDB_OP_COPY) X(MDB_OP_NEG) X(MDB_OP_ABS) X(MDB_OP_SIGN) X(MDB_OP_CEIL) X(MDB_OP_FLOOR)      \
   X(MDB_OP_SIN) X(MDB_OP_COS) X(MDB_OP_TAN) X(MDB_OP_SINH) X(MDB_OP_COSH) X(MDB_OP_TANH)        \
   X(MDB_OP_EXP) X(MDB_OP_LOG) X(MDB_OP_SQRT) X(MDB_OP_RECIP) X(MDB_OP_SQUARE)                   \
-  X(MDB_OP_LOGICAL_NOT) X(MDB_OP_INVERT) X(MDB_OP_ISNAN)
+  X(MDB_OP_LOGICAL_NOT) X(MDB_OP_INVERT) X(MDB_OP_ISNAN) X(MDB_OP_RELU)
 #define MDB_BINARY_OPS(X)                                                                       \
   X(MDB_OP_ADD) X(MDB_OP_SUB) X(MDB_OP_MUL) X(MDB_OP_DIV) X(MDB_OP_POW) X(MDB_OP_MOD)           \
   X(MDB_OP_FLOORDIV) X(MDB_OP_MAXIMUM) X(MDB_OP_MINIMUM) X(MDB_OP_EQ) X(MDB_OP_NE) X(MDB_OP_GT) \

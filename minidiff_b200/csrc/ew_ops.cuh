@@ -159,6 +159,7 @@ __device__ __forceinline__ T apply(T a, T b, T c, T d) {
   else if constexpr (OP == MDB_OP_LOGICAL_NOT) return T(a == 0);
   else if constexpr (OP == MDB_OP_INVERT) { if constexpr (I) return ~a; else return a; }
   else if constexpr (OP == MDB_OP_ISNAN) return T(a != a);
+  else if constexpr (OP == MDB_OP_RELU) return a > 0 ? a : T(0);
   else if constexpr (OP == MDB_OP_ADD) return add_(a, b);
   else if constexpr (OP == MDB_OP_SUB) return sub_(a, b);
   else if constexpr (OP == MDB_OP_MUL) return mul_(a, b);
