@@ -124,7 +124,7 @@ def make_ops(md):
                 return md.matmul(X.T, self.masked(grad))
 
             def grad_b(X, W, b, grad):
-                return md.sum(self.masked(grad), axis=0)
+                return md.sum(self.masked(grad), axis=(0,))   # tuple: sum_grad rejects an int axis (reference quirk)
 
             return [grad_X, grad_W, grad_b]
 
