@@ -125,7 +125,7 @@ int mdb_gemm_knob(int knob, int value) {
     case MDB_GEMM_KNOB_HINT_B: g_knob_hint_b = value; break;
     case MDB_GEMM_KNOB_HINT_C: g_knob_hint_c = value; break;
     case MDB_GEMM_KNOB_STREAMK: g_knob_streamk = value; break;
-    case MDB_GEMM_KNOB_L2_BUDGET_MB: g_knob_l2_budget_mb = value > 0 ? value : 40; break;
+    case MDB_GEMM_KNOB_L2_BUDGET_MB: g_knob_l2_budget_mb = value > 0 ? value : 32; break;
     default: return set_error(MDB_EINVAL, "unknown GEMM knob %d", knob);
   }
   return 0;

@@ -44,7 +44,8 @@
 //   256 tiles on 74 clusters = 3.46 waves -> 3 + 34 tiles split two ways = 3.5 instead of 4).
 // Tile order (raster): groups of `group` tile-rows walked column by column (raster 0) or groups of
 // `group` tile-columns walked row by row (raster 1), so that the clusters of a wave share few
-// distinct operand panels; TMA loads and C stores carry L2 eviction hints chosen by the host.
+// distinct operand panels; TMA loads and C stores can carry L2 eviction hints (off by default: measured
+// useless to harmful, profiles/r02_gemm_dram_traffic.md).
 // Fused epilogue (linear_relu): C = relu?( A@B + bias? ) * (mask_src > 0)?
 constexpr int kPairThreads = 512;
 constexpr int kPairConvWarps = 4, kPairEpiWarps = 8;

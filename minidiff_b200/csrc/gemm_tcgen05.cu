@@ -511,7 +511,7 @@ extern uint64_t g_gemm_path[MDB_GEMM_NPATHS];
 // tuning knobs (mdb_gemm_knob): -1 = automatic
 int g_knob_raster = -1, g_knob_group = -1, g_knob_hint_a = -1, g_knob_hint_b = -1, g_knob_hint_c = -1;
 int g_knob_streamk = -1;          // -1 auto, 0 never, 1 whenever the split is legal
-int g_knob_l2_budget_mb = 40;     // bytes of one operand the tile order tries to keep L2-resident
+int g_knob_l2_budget_mb = 32;     // an operand up to this size is walked whole per band of tiles (stays L2-resident)
 
 constexpr int kPairHi = 4, kPairLo = 3;
 using PairSmem = tc::Smem<tc::PBN, kPairHi, kPairLo>;
@@ -577,27 +577,33 @@ static void plan_pair(tc::PairParams& q, int max_clusters, int* grid_clusters, b
   const double panel = 256.0 * (double)q.K * 4.0;                // one 256-row operand panel, bytes
   const double a_total = (double)q.M * q.K * 4.0, b_total = (double)q.N * q.K * 4.0;
   const double budget = (double)g_knob_l2_budget_mb * 1048576.0;
-  // ---- tile order: keep `group` panels of the SMALLER operand resident in L2 and stream the other
-  // one past them; when not even one panel fits (K = batch in the dW GEMMs) fall back to near-square
-  // waves whose clusters march through k together (every byte is shared inside the wave only)
+  // ---- tile order (measured with ncu, profiles/r02_gemm_dram_traffic.md).  The clusters of a wave march
+  // through k together, so inside a wave every operand panel is fetched from DRAM about once; across
+  // waves the L2 keeps a panel only when the panels of one wave (74 tiles: (rows + cols) * 256*K*4 B)
+  // stay well below its effective capacity -- at K = 4096 they are ~70 MB and nothing survives, with
+  // or without eviction hints (evict_last on the re-used operand changed the DRAM bytes by < 5 %,
+  // evict_first on the streamed one made them 40 % worse: it breaks the sharing INSIDE the wave).
+  //   * smaller operand <= budget (32 MB): walk ALL its panels per band, the other operand streams
+  //     past once (fwd1 / dh2 / fwd3 of the C4 step: DRAM bytes 0.99-1.19 x algorithmic);
+  //   * otherwise near-square waves (8 x 9.25 tiles), the minimum of (rows + cols).
   int raster, group, hint_a = 0, hint_b = 0;
-  const int fit = (int)(budget / panel);
-  if (fit >= 1) {
-    if (b_total <= a_total) {
-      raster = 1; group = std::min(q.tiles_n, fit); hint_b = 2; hint_a = 1;
-    } else {
-      raster = 0; group = std::min(q.tiles_m, fit); hint_a = 2; hint_b = 1;
-    }
+  (void)panel;
+  if (std::min(a_total, b_total) <= budget) {
+    if (b_total <= a_total) { raster = 1; group = q.tiles_n; }
+    else { raster = 0; group = q.tiles_m; }
   } else {
-    raster = 0; group = std::min(q.tiles_m, 8);
+    raster = b_total < a_total ? 1 : 0;
+    group = 8;
   }
+  group = std::min(group, raster ? q.tiles_n : q.tiles_m);
   if (g_knob_raster >= 0) raster = g_knob_raster;
   if (g_knob_group > 0) group = std::min(g_knob_group, raster ? q.tiles_n : q.tiles_m);
   q.raster = raster; q.group = std::max(group, 1);
   q.hint_a = g_knob_hint_a >= 0 ? g_knob_hint_a : hint_a;
   q.hint_b = g_knob_hint_b >= 0 ? g_knob_hint_b : hint_b;
   const double c_bytes = (double)q.M * q.N * 4.0;
-  q.hint_c = g_knob_hint_c >= 0 ? g_knob_hint_c : ((!q.accumulate && c_bytes > 32.0 * 1048576.0) ? 1 : 0);
+  (void)c_bytes;
+  q.hint_c = g_knob_hint_c >= 0 ? g_knob_hint_c : 0;
   // ---- work split
   q.dp_tiles = tiles; q.sk_clusters = 0; q.sk_share = 0;
   q.sk_partials = nullptr; q.sk_flags = nullptr;

@@ -70,6 +70,10 @@ variants = [("old_r0g8", dict(raster=0, group=8, hint_a=0, hint_b=0, hint_c=0, s
             ("r1g16", dict(raster=1, group=16, streamk=0)),
             ("r0g4", dict(raster=0, group=4, streamk=0)),
             ("r0g16", dict(raster=0, group=16, streamk=0))]
+if os.environ.get("SWEEP") == "flags":
+    # kernel-flag A/B (mdb_gemm_tune bits) instead of planner knobs
+    variants = [("base", dict(_flags=4 | 32)), ("sleepwait", dict(_flags=4 | 32 | 256)), ("base2", dict(_flags=4 | 32)),
+                ("sleepwait2", dict(_flags=4 | 32 | 256))]
 check(lib.mdb_gemm_tune(4 | 32))
 for name, (M, K, N), ta, tb in shapes:
     if only and name not in only:
@@ -87,6 +91,8 @@ for name, (M, K, N), ta, tb in shapes:
     plans = {}
     for _ in range(rounds):
         for vn, kw in variants:
+            kw = dict(kw)
+            check(lib.mdb_gemm_tune(kw.pop("_flags", 4 | 32)))
             setk(**kw)
             res[vn].append(timeit(fn, reps))
             plans[vn] = plan()
