@@ -32,7 +32,8 @@ extern "C" {
 #define MDB_ABI_VERSION 1
 
 /* status codes */
-enum { MDB_OK = 0, MDB_EINVAL = 1, MDB_ECUDA = 2, MDB_ENOMEM = 3, MDB_ENOTSUP = 4, MDB_ECOMM = 5 };
+enum { MDB_OK = 0, MDB_EINVAL = 1, MDB_ECUDA = 2, MDB_ENOMEM = 3, MDB_ENOTSUP = 4, MDB_ECOMM = 5,
+       MDB_EINDEX = 6 /* data-dependent index out of range: the shim raises IndexError */ };
 
 /* element types (mirrors the dtype objects a backend exports: backend/numpy.py:188-200) */
 typedef enum {
@@ -164,6 +165,10 @@ int mdb_elementwise_reduce(int op, const mdb_array* out, int n_in, const mdb_arr
  * tcgen05 tensor cores when shapes allow, else an fp32 CUDA-core kernel.
  * C = A@B (accumulate=0) or C += A@B (accumulate=1, the in-place form of topology.py:101-104). */
 int mdb_gemm(const mdb_array* c, const mdb_array* a, const mdb_array* b, int accumulate);
+/* np.matmul for stacked and/or float64 operands: c[..., M, N] = a[..., M, K] @ b[..., K, N], all three
+ * given with the SAME rank (leading batch axes of a / b may have extent 1 = broadcast), float32 or
+ * float64, any strides; every matrix of the batch in ONE launch of a CUDA-core kernel (O(M*N) memory). */
+int mdb_gemm_batched(const mdb_array* c, const mdb_array* a, const mdb_array* b);
 int mdb_gemm_tune(int flags);                     /* kernel tuning switches for A/B measurements   */
 int mdb_gemm_config(int force_path);              /* 0 auto, 1 CUDA-core kernel only, 2 tensor-core
                                                      kernel only (tests) */
@@ -175,6 +180,7 @@ enum { MDB_GEMM_PATH_SIMT = 0,        /* fp32 CUDA-core kernel (small / odd shap
        MDB_GEMM_PATH_TC_PRESPLIT = 2, /* tcgen05 single-CTA after a hi/lo gather pre-pass           */
        MDB_GEMM_PATH_TC_PAIR = 3,     /* tcgen05 cta_group::2, 256x256 tiles, whole tiles per pair  */
        MDB_GEMM_PATH_TC_PAIR_STREAMK = 4, /* same kernel, k-range split across pairs (stream-K)     */
+       MDB_GEMM_PATH_SIMT_BATCHED = 5,    /* batched / float64 CUDA-core kernel (mdb_gemm_batched)    */
        MDB_GEMM_NPATHS = 8 };
 int mdb_gemm_stats(uint64_t* counts, int reset);
 /* measurement knobs of the CTA-pair kernel's planner (-1 = automatic): tile order, L2 eviction hints
@@ -204,11 +210,40 @@ int mdb_gemm_fused(const mdb_array* c, const mdb_array* a, const mdb_array* b, i
  *            the np.add.at semantics getitem_grad relies on: ops/definitions.py:186-189)
  * idx is a contiguous int64 vector; negative entries wrap.  src of scatter may broadcast
  * (stride 0). */
+/* When the indexed array's shape[0] is MDB_ROWS_ARE_OFFSETS, idx holds ELEMENT OFFSETS that
+ * mdb_index_offsets has already validated (signed: views with negative strides work); they are used
+ * as they are, without wrapping or clamping. */
+#define MDB_ROWS_ARE_OFFSETS ((int64_t)1 << 62)
 int mdb_gather_rows(const mdb_array* out, const mdb_array* src, const mdb_array* idx);
 int mdb_scatter_rows(const mdb_array* dst, const mdb_array* src, const mdb_array* idx, int add);
 
-/* counter-based RNG on device (rand / randn: backend/numpy.py:131-134) */
+/* off (+)= wrap(idx) * stride for an integer index array `idx` (any integer dtype, given broadcast to
+ * off's shape) over an axis of `extent` elements: negative indices count from the end, anything outside
+ * [-extent, extent) makes the call return MDB_EINDEX with NumPy's message ("index N is out of bounds
+ * for axis with size E": backend/numpy.py:73-75 raises IndexError there).  The check reads one flag
+ * back (stream sync); inside a CUDA-graph capture it cannot, and offending indices are clamped. */
+int mdb_index_offsets(const mdb_array* off, const mdb_array* idx, int64_t extent, int64_t stride, int accumulate);
+/* stream compaction: flat positions of the non-zero entries of a contiguous bool mask, in order, into
+ * out_indices (int64, room for every element); *count = how many (argwhere, ops/definitions.py:279-290;
+ * boolean-mask getitem / setitem, backend/numpy.py:73-75).  Synchronises (the size is data-dependent). */
+int mdb_nonzero(const mdb_array* mask, const mdb_array* out_indices, int64_t* count);
+/* unravel_index (tensor.py:509-515): out is int64 [ndim, n]; out-of-range -> MDB_EINVAL like NumPy's ValueError */
+int mdb_unravel_index(const mdb_array* out, const mdb_array* indices, int ndim, const int64_t* dims);
+/* isin (tensor.py:503-507): out[i] = (elements[i] in test) != invert; integer pairs compare as int64,
+ * anything else as float64 */
+int mdb_isin(const mdb_array* out, const mdb_array* elements, const mdb_array* test, int invert);
+
+/* counter-based RNG on device (rand / randn / randint / binomial / permutation / choice:
+ * backend/numpy.py:131-138, tensor.py:608-659); Philox4x32-10, (seed, offset) select the stream */
 int mdb_random(const mdb_array* out, int normal, uint64_t seed, uint64_t offset);
+int mdb_random_bits(const mdb_array* out, uint64_t seed, uint64_t offset);            /* raw 32-bit words */
+int mdb_randint(const mdb_array* out, int64_t low, int64_t high, uint64_t seed, uint64_t offset);
+int mdb_binomial(const mdb_array* out, int64_t trials, const mdb_array* p, uint64_t seed, uint64_t offset);
+/* out = uniformly random permutation of 0..n-1 (device bitonic sort of (random word, i) keys) */
+int mdb_permutation(const mdb_array* out, const mdb_array* bits);
+/* weighted choice: inclusive float64 scan of the weights, then out[i] = searchsorted(cdf / cdf[-1], u[i], "right") */
+int mdb_cumsum_f64(const mdb_array* out, const mdb_array* in);
+int mdb_searchsorted_cdf(const mdb_array* out, const mdb_array* cdf, const mdb_array* u);
 
 /* ---- data-parallel exchange (config 4; no counterpart in the reference: SURVEY 2.1) --------- */
 int mdb_comm_unique_id(void* id128, const char* nccl_lib_path);          /* rank 0               */

@@ -35,7 +35,7 @@ class MdbArray(C.Structure):
 
 
 # status codes
-OK, EINVAL, ECUDA, ENOMEM, ENOTSUP, ECOMM = range(6)
+OK, EINVAL, ECUDA, ENOMEM, ENOTSUP, ECOMM, EINDEX = range(7)
 
 # dtype codes (mdb_dtype)
 BOOL, U8, I8, I16, I32, I64, F32, F64, U16, U32, U64, F16 = range(12)
@@ -92,6 +92,7 @@ _SIGS = {
     "mdb_reduce": (C.c_int, [C.c_int, _A, _A, C.c_uint32]),
     "mdb_elementwise_reduce": (C.c_int, [C.c_int, _A, C.c_int, _A, C.c_int]),
     "mdb_gemm": (C.c_int, [_A, _A, _A, C.c_int]),
+    "mdb_gemm_batched": (C.c_int, [_A, _A, _A]),
     "mdb_gemm_config": (C.c_int, [C.c_int]),
     "mdb_gemm_tune": (C.c_int, [C.c_int]),
     "mdb_gemm_stats": (C.c_int, [_P(C.c_uint64), C.c_int]),
@@ -101,6 +102,16 @@ _SIGS = {
     "mdb_gather_rows": (C.c_int, [_A, _A, _A]),
     "mdb_scatter_rows": (C.c_int, [_A, _A, _A, C.c_int]),
     "mdb_random": (C.c_int, [_A, C.c_int, C.c_uint64, C.c_uint64]),
+    "mdb_random_bits": (C.c_int, [_A, C.c_uint64, C.c_uint64]),
+    "mdb_randint": (C.c_int, [_A, C.c_int64, C.c_int64, C.c_uint64, C.c_uint64]),
+    "mdb_binomial": (C.c_int, [_A, C.c_int64, _A, C.c_uint64, C.c_uint64]),
+    "mdb_permutation": (C.c_int, [_A, _A]),
+    "mdb_cumsum_f64": (C.c_int, [_A, _A]),
+    "mdb_searchsorted_cdf": (C.c_int, [_A, _A, _A]),
+    "mdb_index_offsets": (C.c_int, [_A, _A, C.c_int64, C.c_int64, C.c_int]),
+    "mdb_nonzero": (C.c_int, [_A, _A, _P(C.c_int64)]),
+    "mdb_unravel_index": (C.c_int, [_A, _A, C.c_int, _P(C.c_int64)]),
+    "mdb_isin": (C.c_int, [_A, _A, _A, C.c_int]),
     "mdb_comm_unique_id": (C.c_int, [C.c_void_p, C.c_char_p]),
     "mdb_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_char_p]),
     "mdb_comm_allreduce_f32": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int]),
@@ -135,6 +146,8 @@ def check(rc: int) -> None:
         raise MemoryError(msg)
     if rc == ENOTSUP:
         raise NotImplementedError(msg)
+    if rc == EINDEX:
+        raise IndexError(msg)
     raise RuntimeError(f"minidiff_b200: {msg}")
 
 

@@ -140,9 +140,34 @@ def _ew(op: str, out_dtype, *operands) -> DeviceArray:
     return _launch_ew(op, DeviceArray.empty(shape, out_dtype), operands)
 
 
+def _byte_extent(a: DeviceArray):
+    lo = hi = 0
+    for e, st in zip(a.shape, a.estrides):
+        if e == 0:
+            return a.ptr, a.ptr
+        if st < 0:
+            lo += (e - 1) * st
+        else:
+            hi += (e - 1) * st
+    return a.ptr + lo * a.itemsize, a.ptr + (hi + 1) * a.itemsize
+
+
+def _clashes(out: DeviceArray, x) -> bool:
+    """True when writing `out` elementwise while reading `x` is a hazard: same allocation, byte ranges
+    intersect, and x is not the very same view (exact aliasing is what the in-place kernels support).
+    NumPy detects such overlap and buffers the operand (`a += a.T`, `a[1:] = a[:-1]`, `x -= x[::-1]`)."""
+    if not isinstance(x, DeviceArray) or x._st is not out._st:
+        return False
+    if x.ptr == out.ptr and x.shape == out.shape and x.estrides == out.estrides:
+        return False
+    lo_o, hi_o = _byte_extent(out)
+    lo_x, hi_x = _byte_extent(x)
+    return lo_o < hi_x and lo_x < hi_o
+
+
 def elementwise_into(op: str, out: DeviceArray, *operands) -> DeviceArray:
     """`out = op(*operands)` written in place (out may be operands[0]): the `+=` family."""
-    operands = [_operand(o) for o in operands]
+    operands = [copy_(o) if _clashes(out, o) else o for o in (_operand(o) for o in operands)]
     rdt = result_dtype(*operands)
     if rdt != out.dtype and not np.can_cast(rdt, out.dtype, casting="same_kind"):
         raise TypeError(f"Cannot cast ufunc '{op.lower()}' output from {rdt!r} to {out.dtype!r} "
@@ -158,6 +183,10 @@ def copy_into(dst: DeviceArray, src) -> None:
     """dst[...] = src with broadcasting + dtype cast (basic `__setitem__`, astype, materialising)."""
     src = _operand(src)
     if isinstance(src, DeviceArray):
+        if _clashes(dst, src):                      # overlapping views of one allocation: buffer the source
+            tmp = DeviceArray.empty(src.shape, src.dtype)
+            check(lib.mdb_copy(_byref(tmp.d), _byref(src.d)))
+            src = tmp
         check(lib.mdb_copy(_byref(dst.d), _byref(src.d)))
     else:
         d = MdbArray()
@@ -621,6 +650,26 @@ def _gemm_fused(a: DeviceArray, b: DeviceArray, bias=None, relu=False, mask_src=
     return out
 
 
+def _gemm_batched(xv: DeviceArray, yv: DeviceArray) -> DeviceArray:
+    """np.matmul for stacked and/or float64 operands: every matrix of the (broadcast) batch in ONE
+    launch of the CUDA-core kernel (C ABI mdb_gemm_batched); O(M*N) memory per matrix."""
+    if xv.shape[-1] != yv.shape[-2]:
+        raise ValueError(
+            f"matmul: Input operand 1 has a mismatch in its core dimension 0, with gufunc signature "
+            f"(n?,k),(k,m?)->(n?,m?) (size {yv.shape[-2]} is different from {xv.shape[-1]})")
+    batch = broadcast_shapes([xv.shape[:-2], yv.shape[:-2]])
+    nb = len(batch)
+    xa = xv.view((1,) * (nb - (xv.ndim - 2)) + xv.shape, (0,) * (nb - (xv.ndim - 2)) + xv.estrides)
+    ya = yv.view((1,) * (nb - (yv.ndim - 2)) + yv.shape, (0,) * (nb - (yv.ndim - 2)) + yv.estrides)
+    out = DeviceArray.empty(batch + (xv.shape[-2], yv.shape[-1]), xv.dtype)
+    if out.size:
+        if xv.shape[-1] == 0:
+            copy_into(out, 0)
+        else:
+            check(lib.mdb_gemm_batched(_byref(out.d), _byref(xa.d), _byref(ya.d)))
+    return out
+
+
 def matmul(x, y, **_kw):
     x, y = asarray(x), asarray(y)
     if x.ndim == 0 or y.ndim == 0:
@@ -631,14 +680,14 @@ def matmul(x, y, **_kw):
     rdt = result_dtype(x, y)
     x = x if x.dtype == dt else astype(x, dt)
     y = y if y.dtype == dt else astype(y, dt)
-    if dt == F64:  # fp64 storage has no tensor-core path; contract through elementwise+reduce
-        r = _matmul_f64(x, y)
-        return r if rdt == dt else astype(r, rdt)
     xv = x.view((1,) + x.shape, (0,) + x.estrides) if x.ndim == 1 else x
     yv = y.view(y.shape + (1,), y.estrides + (0,)) if y.ndim == 1 else y
-    if xv.ndim == 2 and yv.ndim == 2:
-        r = _gemm(xv, yv)
-    else:  # batched: broadcast leading axes, one GEMM per matrix
+    if dt == F32 and xv.ndim == 2 and yv.ndim == 2:
+        r = _gemm(xv, yv)                 # tcgen05 3xTF32 (CUDA-core kernel for small / odd shapes)
+    elif dt == F32 and xv.shape[-2] * yv.shape[-1] * xv.shape[-1] >= (1 << 24) and len(
+            broadcast_shapes([xv.shape[:-2], yv.shape[:-2]])) <= 2 and math.prod(
+            broadcast_shapes([xv.shape[:-2], yv.shape[:-2]])) <= 64:
+        # a few LARGE stacked matrices: one tensor-core GEMM each beats the batched CUDA-core kernel
         if xv.shape[-1] != yv.shape[-2]:
             raise ValueError("matmul: Input operand 1 has a mismatch in its core dimension 0")
         batch = broadcast_shapes([xv.shape[:-2], yv.shape[:-2]])
@@ -647,27 +696,13 @@ def matmul(x, y, **_kw):
         r = DeviceArray.empty(batch + (xv.shape[-2], yv.shape[-1]), dt)
         for idx in np.ndindex(*batch):
             _gemm(getitem(xb, idx), getitem(yb, idx), out=getitem(r, idx))
+    else:
+        r = _gemm_batched(xv, yv)         # float64 / integer operands and stacked matrices: one launch
     if x.ndim == 1:
         r = squeeze(r, axis=-2)
     if y.ndim == 1:
         r = squeeze(r, axis=-1)
     return r if rdt == dt else astype(r, rdt)
-
-
-def _matmul_f64(x, y):
-    xv = x.view((1,) + x.shape, (0,) + x.estrides) if x.ndim == 1 else x
-    yv = y.view(y.shape + (1,), y.estrides + (0,)) if y.ndim == 1 else y
-    if xv.shape[-1] != yv.shape[-2]:
-        raise ValueError(
-            f"matmul: Input operand 1 has a mismatch in its core dimension 0, with gufunc signature "
-            f"(n?,k),(k,m?)->(n?,m?) (size {yv.shape[-2]} is different from {xv.shape[-1]})")
-    prod_ = _ew("MUL", F64, expand_dims(xv, -1), expand_dims(yv, -3))   # [..., m, k, n]
-    r = sum_(prod_, axis=-2)
-    if x.ndim == 1:
-        r = squeeze(r, axis=-2)
-    if y.ndim == 1:
-        r = squeeze(r, axis=-1)
-    return r
 
 
 def dot(a, b, **_kw):
@@ -768,22 +803,26 @@ def _advanced_plan(a: DeviceArray, key):
             raise IndexError("arrays used as indices must be of integer (or boolean) type")
         arrs.append(k)
     bshape = broadcast_shapes([k.shape for k in arrs if isinstance(k, DeviceArray)] or [()])
-    off = None
+    # element offsets, one fused + VALIDATED launch per index array (mdb_index_offsets: wraps negative
+    # indices, raises IndexError for anything outside [-extent, extent) like NumPy does)
+    off = DeviceArray.empty(bshape, I64)
+    const, first = 0, True
     for axis, k in enumerate(arrs):
         e = a.shape[axis]
         if isinstance(k, DeviceArray):
-            k = k if k.dtype == I64 else astype(k, I64)
-            wrapped = _ew("WHERE", I64, less(k, 0), add(k, e), k)
+            kb = k.view((1,) * (len(bshape) - k.ndim) + k.shape, (0,) * (len(bshape) - k.ndim) + k.estrides)
+            check(lib.mdb_index_offsets(_byref(off.d), _byref(kb.d), e, a.estrides[axis], 0 if first else 1))
+            first = False
         else:
             i = operator.index(k)
             if not -e <= i < e:
                 raise IndexError(f"index {i} is out of bounds for axis {axis} with size {e}")
-            wrapped = i % e
-        term = multiply(wrapped, a.estrides[axis]) if a.estrides[axis] != 1 else wrapped
-        off = term if off is None else add(off, term)
-    if not isinstance(off, DeviceArray):
-        off = asarray(np.int64(off))
-    off = reshape(copy_(broadcast_to(off, bshape)), (-1,))
+            const += (i % e) * a.estrides[axis]
+    if first:
+        copy_into(off, const)
+    elif const:
+        elementwise_into("ADD", off, off, const)
+    off = reshape(off, (-1,))
     k = len(arrs)
     return off, bshape, a.shape[k:], a.estrides[k:]
 
@@ -793,7 +832,7 @@ def _rows_view(a: DeviceArray, tshape, tstrides) -> MdbArray:
     d.ptr = a.ptr
     d.dtype = dtype_code(a.dtype)
     d.ndim = 1 + len(tshape)
-    d.shape[0] = 1 << 62
+    d.shape[0] = 1 << 62          # MDB_ROWS_ARE_OFFSETS: the index vector holds validated element offsets
     d.strides[0] = 1
     for i, (e, s) in enumerate(zip(tshape, tstrides)):
         d.shape[i + 1] = e
@@ -802,9 +841,15 @@ def _rows_view(a: DeviceArray, tshape, tstrides) -> MdbArray:
 
 
 def _mask_to_indices(mask: DeviceArray) -> DeviceArray:
-    """Boolean-mask selection has a data-dependent output size, so (like every GPU array library)
-    the mask is read back once to size the result; the selection itself runs on the device."""
-    return asarray(np.flatnonzero(mask.numpy()).astype(np.int64))
+    """Flat positions of the True entries of `mask`, in order: device stream compaction (ballot + scan,
+    C ABI mdb_nonzero).  Only the COUNT comes back to the host (8 bytes) -- the result size is
+    data-dependent, so like every GPU array library this synchronises once."""
+    m = mask if mask.dtype == BOOL else not_equal(mask, 0)
+    m = m if m.is_c_contiguous() else copy_(m)
+    buf = DeviceArray.empty((m.size,), I64)
+    n = C.c_int64(0)
+    check(lib.mdb_nonzero(_byref(m.d), _byref(buf.d), _byref(n)))
+    return buf.view((n.value,), (1,))
 
 
 def getitem(a, key):
@@ -877,18 +922,18 @@ def index_add(a, indices, b=None):
 def _along_axis_offsets(arr: DeviceArray, indices: DeviceArray, axis: int) -> DeviceArray:
     if indices.ndim != arr.ndim:
         raise ValueError("`indices` and `arr` must have the same number of dimensions")
-    e = arr.shape[axis]
-    idx = indices if indices.dtype == I64 else astype(indices, I64)
-    idx = _ew("WHERE", I64, less(idx, 0), add(idx, e), idx)
-    off = multiply(idx, arr.estrides[axis])
+    if indices.dtype.kind not in "iu":
+        raise IndexError("`indices` must be an integer array")
+    off = DeviceArray.empty(indices.shape, I64)
+    check(lib.mdb_index_offsets(_byref(off.d), _byref(indices.d), arr.shape[axis], arr.estrides[axis], 0))
     for d in range(arr.ndim):
         if d == axis or indices.shape[d] == 1 and arr.shape[d] == 1:
             continue
         shp = [1] * arr.ndim
         shp[d] = indices.shape[d]
         grid = reshape(arange(indices.shape[d]), shp)
-        off = add(off, multiply(grid, arr.estrides[d]))
-    return reshape(copy_(broadcast_to(off, indices.shape)), (-1,))
+        elementwise_into("ADD", off, off, multiply(grid, arr.estrides[d]))
+    return reshape(off, (-1,))
 
 
 def take_along_axis(arr, indices, axis=None):
@@ -1070,22 +1115,43 @@ def vmap(fun):
     return mapped
 
 
-# ---- host-assisted helpers: results whose size or content is index bookkeeping, not arithmetic
-def argwhere(a):
-    return asarray(np.argwhere(asarray(a).numpy()))
-
-
-def isin(element, test_elements, **kw):
-    e = element.numpy() if isinstance(element, DeviceArray) else element
-    t = _to_host_nested(test_elements) if isinstance(test_elements, (list, tuple)) else (
-        test_elements.numpy() if isinstance(test_elements, DeviceArray) else test_elements)
-    r = np.isin(e, t, **kw)
-    return asarray(r) if isinstance(element, DeviceArray) else r
-
-
+# ---- data-dependent helpers, on the device (C ABI mdb_nonzero / mdb_unravel_index / mdb_isin)
 def unravel_index(indices, shape):
-    i = indices.numpy() if isinstance(indices, DeviceArray) else indices
-    return tuple(asarray(x) for x in np.unravel_index(i, shape))
+    idx = asarray(indices)
+    if idx.dtype.kind not in "iu":
+        raise TypeError("only int indices permitted")
+    dims = (int(shape),) if isinstance(shape, (int, np.integer)) else tuple(int(s_) for s_ in shape)
+    if not 1 <= len(dims) <= _lib.MAX_DIMS:
+        raise ValueError(f"unravel_index supports 1..{_lib.MAX_DIMS} dimensions on device")
+    flat = idx if idx.is_c_contiguous() else copy_(idx)
+    out = DeviceArray.empty((len(dims), flat.size), I64)
+    check(lib.mdb_unravel_index(_byref(out.d), _byref(flat.d), len(dims), (C.c_int64 * len(dims))(*dims)))
+    return tuple(reshape(getitem(out, d), idx.shape) for d in range(len(dims)))
+
+
+def argwhere(a):
+    a = asarray(a)
+    flat = _mask_to_indices(reshape(a, (-1,)) if a.ndim else reshape(a, (1,)))
+    if a.ndim == 0:
+        return DeviceArray.empty((flat.shape[0], 0), I64)
+    if a.ndim == 1:
+        return reshape(copy_(flat), (-1, 1))
+    coords = DeviceArray.empty((a.ndim, flat.shape[0]), I64)
+    if flat.shape[0]:
+        check(lib.mdb_unravel_index(_byref(coords.d), _byref(flat.d), a.ndim, (C.c_int64 * a.ndim)(*a.shape)))
+    return copy_(coords.T)                      # (n, ndim), C-contiguous like NumPy's
+
+
+def isin(element, test_elements, assume_unique=False, invert=False, **_kw):
+    scalar_in = not isinstance(element, (DeviceArray, np.ndarray, list, tuple))
+    e = asarray(element)
+    t = asarray(test_elements)
+    e_c = e if e.is_c_contiguous() else copy_(e)
+    t_c = reshape(t if t.is_c_contiguous() else copy_(t), (-1,))
+    out = DeviceArray.empty(e.shape, BOOL)
+    if out.size:
+        check(lib.mdb_isin(_byref(out.d), _byref(e_c.d), _byref(t_c.d), 1 if invert else 0))
+    return out.numpy().reshape(()).item() if scalar_in and not isinstance(element, DeviceArray) else out
 
 
 def save(file, arr, **kw):
@@ -1124,28 +1190,54 @@ def randint(low, high=None, size=None, dtype=int):
     if high <= low:
         raise ValueError("low >= high")
     shape = () if size is None else _shape_arg(size)
-    u = _random(shape, False)
-    r = astype(floor(add(multiply(u, high - low), low)), np.dtype(dtype))
-    return r
+    out = DeviceArray.empty(shape, np.dtype(dtype))
+    if out.dtype.kind not in "iu":
+        raise TypeError(f"Unsupported dtype {out.dtype!r} for randint")
+    check(lib.mdb_randint(_byref(out.d), int(low), int(high), _rng_state["seed"], _rng_state["offset"]))
+    _rng_state["offset"] += (out.size + 1) // 2
+    return out
 
 
 def binomial(n, p, size=None):
+    """Sum of n Bernoulli(p) draws per output, one launch (C ABI mdb_binomial); p scalar or array."""
     n = int(n.item() if isinstance(n, DeviceArray) else n)
+    if n < 0:
+        raise ValueError("n < 0")
     shape = () if size is None else _shape_arg(size)
-    if isinstance(p, DeviceArray):
+    pd = MdbArray()
+    keep = None
+    if isinstance(p, (DeviceArray, np.ndarray, list, tuple)):
+        p = asarray(p)
         shape = broadcast_shapes([shape, p.shape]) if size is not None else p.shape
-    acc = zeros(shape, dtype=np.int64)
-    for _ in range(n):
-        acc = add(acc, astype(less(_random(shape, False), p), np.int64))
-    return acc
+        keep = copy_(broadcast_to(p, shape))
+        pd = keep.d
+    else:
+        if not 0.0 <= float(p) <= 1.0:
+            raise ValueError("p < 0, p > 1 or p is NaN")
+        _fill_imm(pd, float(p))
+    out = DeviceArray.empty(shape, I64)
+    check(lib.mdb_binomial(_byref(out.d), n, _byref(pd), _rng_state["seed"], _rng_state["offset"]))
+    _rng_state["offset"] += max(out.size, 1) * ((n + 3) // 4)
+    return out
+
+
+def _random_permutation_indices(n: int) -> DeviceArray:
+    """uniformly random permutation of 0..n-1 on the device: bitonic sort of (random word, i) keys"""
+    bits = DeviceArray.empty((max(n, 1),), np.dtype(np.uint32))
+    check(lib.mdb_random_bits(_byref(bits.d), _rng_state["seed"], _rng_state["offset"]))
+    _rng_state["offset"] += (n + 3) // 4
+    out = DeviceArray.empty((n,), I64)
+    check(lib.mdb_permutation(_byref(out.d), _byref(bits.d)))
+    return out
 
 
 def permutation(x):
     if isinstance(x, (int, np.integer)):
-        x = arange(int(x))
+        return _random_permutation_indices(int(x))
     x = asarray(x)
-    keys = _random((x.shape[0],), False).numpy()          # device-generated keys, order on host
-    return getitem(x, asarray(np.argsort(keys, kind="stable").astype(np.int64)))
+    if x.ndim == 0:
+        raise IndexError("x must be an integer or at least 1-dimensional")
+    return getitem(x, _random_permutation_indices(x.shape[0]))
 
 
 def shuffle(x):
@@ -1162,14 +1254,19 @@ def choice(a, size=None, replace=True, p=None):
     elif p is None:
         if k > n:
             raise ValueError("Cannot take a larger sample than population when 'replace=False'")
-        idx = getitem(permutation(n), slice(0, k))
+        idx = getitem(_random_permutation_indices(n), slice(0, k))
     else:
-        pp = p.numpy() if isinstance(p, DeviceArray) else np.asarray(p, dtype=np.float64)
         if not replace:
             raise NotImplementedError("weighted sampling without replacement")
-        cdf = np.cumsum(pp) / np.sum(pp)
-        u = _random((k,), False).numpy()
-        idx = asarray(np.searchsorted(cdf, u, side="right").astype(np.int64))
+        pp = asarray(p)
+        if pp.shape != (n,):
+            raise ValueError("'a' and 'p' must have same size")
+        pp = pp if pp.is_c_contiguous() else copy_(pp)
+        cdf = DeviceArray.empty((n,), F64)
+        check(lib.mdb_cumsum_f64(_byref(cdf.d), _byref(pp.d)))      # inclusive scan of the weights
+        u = _random((k,), False)
+        idx = DeviceArray.empty((k,), I64)
+        check(lib.mdb_searchsorted_cdf(_byref(idx.d), _byref(cdf.d), _byref(u.d)))
     return reshape(getitem(pool, idx), shape)
 
 

@@ -1,6 +1,8 @@
 // matmul (backend/numpy.py:84) and its two gradient GEMMs (ops/definitions.py:487-492):
 // dispatcher + the fp32 CUDA-core kernel used for shapes the tcgen05 path does not take
 // (small / unaligned operands, e.g. the reference tests' 10x30 @ 30x20).
+#include <algorithm>
+
 #include "mdb_common.cuh"
 
 namespace mdb {
@@ -69,6 +71,74 @@ __global__ void __launch_bounds__(256) sgemm_simt(int M, int N, int K, const flo
         *p = ACC ? __fadd_rn(*p, acc[i][j]) : acc[i][j];
       }
     }
+}
+
+// Batched / double-precision matmul on the CUDA cores: the same 64x64x16 tiling for T = float or double,
+// every operand addressed through element strides (views, broadcast batch axes with stride 0), all
+// matrices of the batch in ONE launch (grid.z walks the flattened batch).  Stands behind matmul for
+// float64 / integer operands (NumPy's default dtype: Tensor(python floats), zeros, rand ...) and for
+// stacked operands (backend/numpy.py:84 is np.matmul, which broadcasts leading axes).
+struct BatchParams {
+  int M, N, K, nbatch_dims;
+  int64_t bshape[MDB_MAX_DIMS], sa[MDB_MAX_DIMS], sb[MDB_MAX_DIMS], sc[MDB_MAX_DIMS];   // batch axes
+  int64_t sam, sak, sbk, sbn, scm, scn;
+  int64_t batches;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) gemm_simt_batched(const BatchParams p, const T* __restrict__ A,
+                                                         const T* __restrict__ B, T* C) {
+  constexpr int BM = 64, BN = 64, BK = 16;
+  __shared__ T As[BK][BM + 4];
+  __shared__ T Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int tr = (tid / 16) * 4, tc = (tid % 16) * 4;
+  const bool a_k_fast = (p.sak == 1), b_n_fast = (p.sbn == 1);
+  for (int64_t batch = blockIdx.z; batch < p.batches; batch += gridDim.z) {
+    int64_t rem = batch, oa = 0, ob = 0, oc = 0;
+    for (int d = p.nbatch_dims - 1; d >= 0; --d) {
+      const int64_t q = rem / p.bshape[d], i = rem - q * p.bshape[d];
+      rem = q;
+      oa += i * p.sa[d]; ob += i * p.sb[d]; oc += i * p.sc[d];
+    }
+    const T* Ab = A + oa;
+    const T* Bb = B + ob;
+    T* Cb = C + oc;
+    T acc[4][4] = {};
+    for (int k0 = 0; k0 < p.K; k0 += BK) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int e = tid + i * 256;
+        const int mm = a_k_fast ? e / BK : e % BM, kk = a_k_fast ? e % BK : e / BM;
+        const int gm = m0 + mm, gk = k0 + kk;
+        As[kk][mm] = (gm < p.M && gk < p.K) ? Ab[(int64_t)gm * p.sam + (int64_t)gk * p.sak] : T(0);
+        const int nn = b_n_fast ? e % BN : e / BK, kb = b_n_fast ? e / BN : e % BK;
+        const int gn = n0 + nn, gkb = k0 + kb;
+        Bs[kb][nn] = (gn < p.N && gkb < p.K) ? Bb[(int64_t)gkb * p.sbk + (int64_t)gn * p.sbn] : T(0);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) {
+        T a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = As[kk][tr + i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tc + j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int gm = m0 + tr + i, gn = n0 + tc + j;
+        if (gm < p.M && gn < p.N) Cb[(int64_t)gm * p.scm + (int64_t)gn * p.scn] = acc[i][j];
+      }
+  }
 }
 
 static int gemm_simt(const mdb_array* c, const mdb_array* a, const mdb_array* b, int accumulate) {
@@ -166,6 +236,48 @@ int mdb_gemm_fused(const mdb_array* c, const mdb_array* a, const mdb_array* b, i
   }
   ProfScope prof(PROF_GEMM, 2.0 * (double)a->shape[0] * (double)a->shape[1] * (double)b->shape[1]);
   return gemm_tcgen05(c, a, b, accumulate, &epi);
+}
+
+int mdb_gemm_batched(const mdb_array* c, const mdb_array* a, const mdb_array* b) {
+  MDB_TRY(ensure_init());
+  MDB_REQUIRE(a && b && c && a->ptr && b->ptr && c->ptr, "gemm_batched: device arrays required");
+  MDB_REQUIRE(a->ndim >= 2 && a->ndim == b->ndim && a->ndim == c->ndim, "gemm_batched: operands must share their rank (>= 2)");
+  MDB_REQUIRE(a->dtype == b->dtype && a->dtype == c->dtype && (a->dtype == MDB_F32 || a->dtype == MDB_F64),
+              "gemm_batched: float32 or float64 operands of one dtype required");
+  const int nd = a->ndim, nb = nd - 2;
+  if (a->shape[nd - 1] != b->shape[nd - 2])
+    return set_error(MDB_EINVAL, "matmul: Input operand 1 has a mismatch in its core dimension 0, "
+                     "with gufunc signature (n?,k),(k,m?)->(n?,m?) (size %lld is different from %lld)",
+                     (long long)b->shape[nd - 2], (long long)a->shape[nd - 1]);
+  MDB_REQUIRE(c->shape[nd - 2] == a->shape[nd - 2] && c->shape[nd - 1] == b->shape[nd - 1], "gemm_batched: bad output shape");
+  BatchParams p;
+  p.M = (int)a->shape[nd - 2]; p.K = (int)a->shape[nd - 1]; p.N = (int)b->shape[nd - 1];
+  MDB_REQUIRE(a->shape[nd - 2] < (1ll << 31) && a->shape[nd - 1] < (1ll << 31) && b->shape[nd - 1] < (1ll << 31),
+              "gemm_batched: extents must fit in int32");
+  p.nbatch_dims = nb; p.batches = 1;
+  for (int d = 0; d < nb; ++d) {
+    const int64_t e = c->shape[d];
+    MDB_REQUIRE((a->shape[d] == e || a->shape[d] == 1) && (b->shape[d] == e || b->shape[d] == 1),
+                "gemm_batched: batch axis %d does not broadcast", d);
+    p.bshape[d] = e;
+    p.sa[d] = a->shape[d] == e ? a->strides[d] : 0;
+    p.sb[d] = b->shape[d] == e ? b->strides[d] : 0;
+    p.sc[d] = c->strides[d];
+    p.batches *= e;
+  }
+  p.sam = a->strides[nd - 2]; p.sak = a->strides[nd - 1];
+  p.sbk = b->strides[nd - 2]; p.sbn = b->strides[nd - 1];
+  p.scm = c->strides[nd - 2]; p.scn = c->strides[nd - 1];
+  if (p.batches == 0 || p.M == 0 || p.N == 0) return 0;
+  ProfScope prof(PROF_GEMM, 2.0 * (double)p.batches * p.M * (double)p.K * p.N);
+  dim3 grid((p.N + 63) / 64, (p.M + 63) / 64, (unsigned)std::min<int64_t>(p.batches, 32768));
+  if (a->dtype == MDB_F32)
+    gemm_simt_batched<float><<<grid, 256, 0, g_stream>>>(p, (const float*)a->ptr, (const float*)b->ptr, (float*)c->ptr);
+  else
+    gemm_simt_batched<double><<<grid, 256, 0, g_stream>>>(p, (const double*)a->ptr, (const double*)b->ptr, (double*)c->ptr);
+  MDB_CHECK_LAUNCH();
+  ++g_gemm_path[MDB_GEMM_PATH_SIMT_BATCHED];
+  return 0;
 }
 
 int mdb_gemm(const mdb_array* c, const mdb_array* a, const mdb_array* b, int accumulate) {

@@ -14,6 +14,7 @@ struct RowsParams {
   int64_t ishape[MDB_MAX_DIMS], a_istr[MDB_MAX_DIMS], b_istr[MDB_MAX_DIMS];
   int64_t inner, total;
   int esize, dtype, mode;  // mode 0 gather, 1 scatter-assign, 2 scatter-add
+  int offsets;             // 1: idx holds validated element OFFSETS (mdb_index_offsets), signed, used as is
 };
 
 __global__ void __launch_bounds__(256) rows_kernel(const RowsParams p) {
@@ -21,8 +22,10 @@ __global__ void __launch_bounds__(256) rows_kernel(const RowsParams p) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < p.total; e += stride) {
     int64_t i = e / p.inner, j = e - i * p.inner;
     long long r = p.idx[i];
-    if (r < 0) r += p.a_rows;
-    r = r < 0 ? 0 : (r >= p.a_rows ? p.a_rows - 1 : r);
+    if (!p.offsets) {
+      if (r < 0) r += p.a_rows;
+      r = r < 0 ? 0 : (r >= p.a_rows ? p.a_rows - 1 : r);
+    }
     int64_t ao = r * p.a_row_stride, bo = i * p.b_row_stride;
     for (int d = p.nin - 1; d >= 0; --d) {
       int64_t q = j / p.ishape[d], k = j - q * p.ishape[d];
@@ -68,6 +71,7 @@ static int rows_op(const mdb_array* indexed, const mdb_array* dense, const mdb_a
   RowsParams p;
   p.a = (char*)indexed->ptr; p.b = (char*)dense->ptr; p.idx = (const long long*)idx->ptr;
   p.n_idx = idx->shape[0]; p.a_rows = indexed->shape[0];
+  p.offsets = indexed->shape[0] == MDB_ROWS_ARE_OFFSETS ? 1 : 0;
   p.a_row_stride = indexed->strides[0];
   p.b_row_stride = dense->shape[0] == 1 && idx->shape[0] != 1 ? 0 : dense->strides[0];
   p.nin = indexed->ndim - 1; p.inner = 1;
@@ -132,6 +136,53 @@ __global__ void __launch_bounds__(256) random_kernel(void* out, int dtype, int64
   }
 }
 
+// raw 32-bit words (keys of the permutation sort)
+__global__ void __launch_bounds__(256) random_bits_kernel(uint32_t* out, int64_t n, uint64_t seed, uint64_t offset) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b * 4 < n; b += stride) {
+    uint32_t r[4];
+    philox4x32((uint64_t)b + offset, seed, r);
+    for (int j = 0; j < 4; ++j)
+      if (b * 4 + j < n) out[b * 4 + j] = r[j];
+  }
+}
+
+// integers uniform on [low, low + span): 64 random bits scaled by multiply-high (bias < span / 2^64)
+__global__ void __launch_bounds__(256) randint_kernel(void* out, int dtype, int64_t n, long long low,
+                                                      unsigned long long span, uint64_t seed, uint64_t offset) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b * 2 < n; b += stride) {
+    uint32_t r[4];
+    philox4x32((uint64_t)b + offset, seed, r);
+    for (int j = 0; j < 2; ++j) {
+      const int64_t i = b * 2 + j;
+      if (i >= n) break;
+      const unsigned long long bits = ((unsigned long long)r[2 * j] << 32) | r[2 * j + 1];
+      store_as<long long>(out, dtype, i, low + (long long)__umul64hi(bits, span));
+    }
+  }
+}
+
+// binomial(trials, p): sum of `trials` Bernoulli draws per output (p scalar or one value per output)
+__global__ void __launch_bounds__(256) binomial_kernel(long long* out, int64_t n, long long trials, const void* p_arr,
+                                                       int p_dtype, double p_imm, uint64_t seed, uint64_t offset) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const uint64_t blocks_per = (uint64_t)((trials + 3) / 4);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double p = p_arr ? load_as<double>(p_arr, p_dtype, i) : p_imm;
+    // compare 32 random bits against p scaled to 2^32 (resolution 2.3e-10)
+    const double scaled = p * 4294967296.0;
+    const unsigned long long thr = scaled <= 0.0 ? 0ull : (scaled >= 4294967296.0 ? 4294967296ull : (unsigned long long)scaled);
+    long long c = 0, left = trials;
+    for (uint64_t b = 0; b < blocks_per; ++b) {
+      uint32_t r[4];
+      philox4x32(offset + (uint64_t)i * blocks_per + b, seed, r);
+      for (int j = 0; j < 4 && left > 0; ++j, --left) c += ((unsigned long long)r[j] < thr) ? 1 : 0;
+    }
+    out[i] = c;
+  }
+}
+
 }  // namespace mdb
 
 using namespace mdb;
@@ -143,6 +194,61 @@ int mdb_gather_rows(const mdb_array* out, const mdb_array* src, const mdb_array*
 }
 int mdb_scatter_rows(const mdb_array* dst, const mdb_array* src, const mdb_array* idx, int add) {
   return rows_op(dst, src, idx, add ? 2 : 1);
+}
+
+static int contiguous_out(const mdb_array* out, const char* who) {
+  int64_t st = 1;
+  for (int d = out->ndim - 1; d >= 0; --d) {
+    MDB_REQUIRE(out->shape[d] == 1 || out->strides[d] == st, "%s: output must be contiguous", who);
+    st *= out->shape[d];
+  }
+  return 0;
+}
+
+int mdb_random_bits(const mdb_array* out, uint64_t seed, uint64_t offset) {
+  MDB_TRY(ensure_init());
+  MDB_REQUIRE(out && out->ptr && dtype_size(out->dtype) == 4, "random_bits: 32-bit output required");
+  MDB_TRY(contiguous_out(out, "random_bits"));
+  const int64_t n = numel(out);
+  if (n == 0) return 0;
+  random_bits_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, g_stream>>>((uint32_t*)out->ptr, n, seed, offset);
+  MDB_CHECK_LAUNCH();
+  return 0;
+}
+
+int mdb_randint(const mdb_array* out, int64_t low, int64_t high, uint64_t seed, uint64_t offset) {
+  MDB_TRY(ensure_init());
+  MDB_REQUIRE(out && out->ptr && (out->dtype == MDB_I64 || out->dtype == MDB_I32 || out->dtype == MDB_I16 ||
+                                  out->dtype == MDB_I8 || out->dtype == MDB_U8 || out->dtype == MDB_U16 ||
+                                  out->dtype == MDB_U32 || out->dtype == MDB_U64),
+              "randint: integer output required");
+  MDB_REQUIRE(high > low, "low >= high");
+  MDB_TRY(contiguous_out(out, "randint"));
+  const int64_t n = numel(out);
+  if (n == 0) return 0;
+  randint_kernel<<<grid_for((n + 1) / 2, 256), 256, 0, g_stream>>>(out->ptr, out->dtype, n, low,
+                                                                  (unsigned long long)(high - low), seed, offset);
+  MDB_CHECK_LAUNCH();
+  return 0;
+}
+
+int mdb_binomial(const mdb_array* out, int64_t trials, const mdb_array* p, uint64_t seed, uint64_t offset) {
+  MDB_TRY(ensure_init());
+  MDB_REQUIRE(out && out->ptr && out->dtype == MDB_I64 && p, "binomial: int64 output and a probability required");
+  MDB_REQUIRE(trials >= 0, "n < 0");
+  MDB_TRY(contiguous_out(out, "binomial"));
+  const int64_t n = numel(out);
+  if (p->ptr) {
+    MDB_REQUIRE(numel(p) == n, "binomial: one probability per output (broadcast on the host side)");
+    MDB_TRY(contiguous_out(p, "binomial p"));
+  } else {
+    MDB_REQUIRE(p->imm >= 0.0 && p->imm <= 1.0, "p < 0, p > 1 or p is NaN");
+  }
+  if (n == 0) return 0;
+  binomial_kernel<<<grid_for(n, 256), 256, 0, g_stream>>>((long long*)out->ptr, n, trials, p->ptr, p->dtype, p->imm,
+                                                         seed, offset);
+  MDB_CHECK_LAUNCH();
+  return 0;
 }
 
 int mdb_random(const mdb_array* out, int normal, uint64_t seed, uint64_t offset) {

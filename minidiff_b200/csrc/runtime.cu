@@ -31,8 +31,18 @@ int set_error(int code, const char* fmt, ...) {
 void count_launches(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 int ensure_init() {
-  if (g_device >= 0) return 0;
-  return mdb_init(0);
+  if (g_device < 0) return mdb_init(0);
+  // the CUDA current device is per THREAD: a call from another Python thread must land on the
+  // library's device (LOCAL_RANK != 0 under torchrun), not on device 0
+  static thread_local int bound = -1;
+  if (bound != g_device) {
+    if (cudaSetDevice(g_device) != cudaSuccess) {
+      cudaGetLastError();
+      return set_error(MDB_ECUDA, "cudaSetDevice(%d) failed on this thread", g_device);
+    }
+    bound = g_device;
+  }
+  return 0;
 }
 
 // ---- caching allocator ---------------------------------------------------------------------
@@ -99,6 +109,10 @@ struct Allocator {
     cudaError_t e = cudaMalloc(&p, r);
     if (e != cudaSuccess) {
       cudaGetLastError();
+      // flushing the cache synchronises the stream, which would invalidate an open capture
+      if (capturing)
+        return set_error(MDB_ENOMEM, "out of device memory allocating %zu bytes while capturing a CUDA graph "
+                         "(the cache cannot be flushed inside a capture)", r);
       release_cached();
       e = cudaMalloc(&p, r);
       if (e != cudaSuccess) {
@@ -316,7 +330,7 @@ int mdb_init(int device) {
   MDB_CUDA(cudaSetDevice(device));
   cudaDeviceProp prop;
   MDB_CUDA(cudaGetDeviceProperties(&prop, device));
-  if (prop.major != 10)
+  if (prop.major != 10 || prop.minor != 0)     // the .so carries sm_100a SASS only (no PTX): sm_103 cannot run it
     return set_error(MDB_ENOTSUP, "device %d is sm_%d%d; this library is built for sm_100a only",
                      device, prop.major, prop.minor);
   g_sm_count = prop.multiProcessorCount;
@@ -328,7 +342,15 @@ int mdb_init(int device) {
 int mdb_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (g_device < 0) return 0;
+  if (g_alloc.capturing) return set_error(MDB_EINVAL, "cannot shut down while a CUDA-graph capture is open");
   g_alloc.release_cached();
+  // forget every remaining block (cached fragments and blocks still referenced by live arrays, whose
+  // later mdb_free then reports an unknown pointer instead of corrupting a re-initialised allocator)
+  for (auto& kv : g_alloc.live) { if (!kv.second->prev && !kv.second->next) cudaFree(kv.second->ptr); delete kv.second; }
+  g_alloc.live.clear();
+  for (auto& kv : g_alloc.large_free) delete kv.second;
+  g_alloc.large_free.clear();
+  g_alloc.in_use = g_alloc.cached = 0;
   cudaStreamDestroy(g_stream);
   g_stream = nullptr;
   g_device = -1;

@@ -77,8 +77,13 @@ class DataParallel:
 
     def _allreduce(self, p):
         g = p.grad._data
-        if g.dtype != np.float32 or not g.is_c_contiguous() or not g.writeable:
-            # aliased / broadcast gradient: give it private contiguous storage first
+        # all-reduce IN PLACE only when this sweep provably owns the buffer (a fresh GEMM / reduction
+        # output).  The engine aliases gradients like the reference does -- `a + b` hands the upstream
+        # gradient to both inputs, `reshape` returns it -- so p.grad can be the buffer of an
+        # intermediate's gradient that the compute stream is still reading for the rest of backward:
+        # averaging it in place on the comm stream would be a data race.  Give it private storage first.
+        private = getattr(p, "_grad_private", None) is p.grad
+        if not private or g.dtype != np.float32 or not g.is_c_contiguous() or not g.writeable:
             from minidiff_b200.backend import functions as F
             import minidiff_b200 as md
 
