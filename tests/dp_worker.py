@@ -50,8 +50,27 @@ else:
     Xs, Ys = md.Tensor(X[lo:hi]), md.Tensor(Y[lo:hi])
     for _ in range(2):
         loss = W.mlp_train_step(Xs, Ys, params, 0.01, dp)
+    # a parameter whose gradient ALIASES an intermediate's gradient (same-shape additive term: the
+    # engine hands the upstream gradient buffer to both inputs of `+`, like the reference): the
+    # exchange must not average that shared buffer in place while backward still reads it
+    rng = np.random.default_rng(77)
+    Wa_np = rng.standard_normal((DIMS[0], 48)).astype(np.float32)
+    Pa_np = rng.standard_normal((BATCH // world, 48)).astype(np.float32)
+    Wa, Pa = md.Tensor(Wa_np.copy(), allow_grad=True), md.Tensor(Pa_np.copy(), allow_grad=True)
+    dp2 = DataParallel.__new__(DataParallel)          # second parameter set on the same communicator
+    dp2.__dict__.update(dp.__dict__)
+    dp2.params, dp2._seq, dp2._pending, dp2._flushed = [Wa, Pa], {}, False, False
+    for q in dp2.params:
+        q._grad_hook = dp2._on_grad_ready
+    alias = []
+    for _ in range(3):
+        h = Xs @ Wa + Pa
+        loss_a = md.mean(h ** 2)
+        loss_a.backward()
+        dp2.finish()
+        alias = [Wa.grad.as_numpy(), Pa.grad.as_numpy()]
     if rank == 0:
-        np.savez(out, *[p.as_numpy() for p in params], loss=loss.as_numpy())
+        np.savez(out, *[p.as_numpy() for p in params], loss=loss.as_numpy(), alias_dW=alias[0], alias_dP=alias[1])
     import torch.distributed as dist
 
     dist.barrier()

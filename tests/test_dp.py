@@ -51,3 +51,15 @@ def test_two_gpu_step_matches_single_gpu(tmp_path):
         W.mlp_train_step(md.Tensor(X), md.Tensor(Y), params, 0.01)
     for i, p in enumerate(params):
         np.testing.assert_allclose(got[f"arr_{i}"], p.as_numpy(), rtol=1e-4, atol=1e-6)
+    # aliased-gradient scenario of the worker: expected averages computed with NumPy per shard
+    rng = np.random.default_rng(77)
+    Wa = rng.standard_normal((dims[0], 48)).astype(np.float32)
+    Pa = rng.standard_normal((batch // 2, 48)).astype(np.float32)
+    dW, dP = 0, 0
+    for r_ in range(2):
+        Xs = X[r_ * batch // 2:(r_ + 1) * batch // 2].astype(np.float64)
+        h = Xs @ Wa + Pa
+        g = 2 * h / h.size
+        dW, dP = dW + Xs.T @ g / 2, dP + g / 2
+    np.testing.assert_allclose(got["alias_dW"], dW, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(got["alias_dP"], dP, rtol=1e-4, atol=1e-7)
