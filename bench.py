@@ -43,9 +43,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# ncu --set full capture of one C4 step at N=1 (profiles/r01_ncu_mlp_step_gemm_pair.md): DRAM bytes per GEMM
+# ncu --set full capture of one C4 step at N=1 (profiles/r02_ncu_mlp_step_gemm.md): DRAM bytes per GEMM
 # launch, and the algorithmic figure beside it (each operand read once + C written once, 8 GEMMs/step)
-GEMM_TRAFFIC_BYTES_PER_LAUNCH = 3.854e9
+GEMM_TRAFFIC_BYTES_PER_LAUNCH = 3.676e9
 GEMM_ALGORITHMIC_BYTES_PER_LAUNCH = (
     # fwd1, fwd2, fwd3 (X@W), dW3, dh2, dW2, dh1, dW1 at B=65536, D=(1024,4096,4096,1024)
     sum(4.0 * (m * k + k * n + m * n) for m, k, n in [
@@ -59,7 +59,7 @@ C2_TRAFFIC_SRC = ("dram__bytes_read.sum + dram__bytes_write.sum over the 13 laun
                   "in the 126 MB L2 when the next op reads it)")
 GEMM_TRAFFIC_SRC = ("dram__bytes_read.sum + dram__bytes_write.sum averaged over the 8 GEMM launches of one C4 step "
                     "(ncu --set full, profiles/r02_ncu_mlp_step_gemm.md)")
-C3_TRAFFIC_BYTES_PER_LAUNCH = 2.65e9
+C3_TRAFFIC_BYTES_PER_LAUNCH = 3.129e9
 C3_TRAFFIC_SRC = ("dram__bytes_read.sum + dram__bytes_write.sum per 8192^3 launch of the shipped pair kernel "
                   "(ncu --set full, profiles/r02_ncu_c3_gemm.md)")
 GLOBAL_BATCH = 65536
@@ -323,7 +323,8 @@ def max_over_ranks(dist, x):
 # ------------------------------------------------------------------------------------------------
 # workloads
 # ------------------------------------------------------------------------------------------------
-def bench_mlp(dev, dist, rank, world, steps, warmup, peaks):
+def bench_mlp(dev, dist, rank, world, steps, warmup, peaks, use_graph=False):
+    graph_error = None
     md = dev.md
     from minidiff_b200 import workloads as W
     from minidiff_b200.parallel import DataParallel
@@ -335,18 +336,35 @@ def bench_mlp(dev, dist, rank, world, steps, warmup, peaks):
     dp = DataParallel(params, rank, world) if world > 1 else None
     dp_parity = dp_parity_check(dev, dist, rank, world, dp, X, Y, params, local) if world > 1 else None
 
-    def step():
+    def eager_step():
         return W.mlp_train_step(X, Y, params, LR, dp)
 
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", 0)))
     sampler.start()
     loss = None
     for _ in range(warmup):
-        loss = step()      # same object lifetimes as the timed loop, so the allocator pool has converged
+        loss = eager_step()      # same object lifetimes as the timed loop, so the allocator pool has converged
     dev.sync()
+    # the repeating step as ONE CUDA-graph replay (md.capture_graph, the device-side counterpart of the
+    # reference's caching.reuse_graph): forward, backward, the NCCL exchange on the forked comm stream
+    # and the SGD update are captured once; every replay does the full work of a step
+    graph, step = None, eager_step
+    if use_graph:
+        try:
+            graph = md.capture_graph(eager_step, warmup=0)
+            step = graph.replay
+            for _ in range(2):
+                loss = step()
+            dev.sync()
+        except Exception as exc:                      # capture refused (e.g. NCCL build without graph support)
+            graph, step, graph_error = None, eager_step, repr(exc)
+            for _ in range(2):
+                loss = step()
+            dev.sync()
     # ---- timed region: inputs resident in HBM
     e0, e1 = dev.event(), dev.event()
-    dev.prof(True)
+    if graph is None:
+        dev.prof(True)           # per-class event timing brackets eager launches only
     barrier(dist)
     dev.sync()
     sampler.mark_begin()
@@ -365,11 +383,20 @@ def bench_mlp(dev, dist, rank, world, steps, warmup, peaks):
     mem = dev.mem()
     mem["device_allocs_in_timed_region"] = mem["device_allocs"] - allocs0
     clocks = sampler.stop()
+    if graph is not None:
+        # the per-class split (roofline of the GEMM class) comes from an eager pass of the same step right
+        # after the timed region: CUDA events cannot bracket kernels inside a graph replay
+        dev.gemm_paths(reset=True)
+        dev.prof(True)
+        for _ in range(min(steps, 5)):
+            eager_step()
+        dev.sync()
     gemm_ms, gemm_n, gemm_flops = dev.prof_read(2)
     ew_ms, ew_n, ew_bytes = dev.prof_read(0)
     red_ms, red_n, red_bytes = dev.prof_read(1)
     dev.prof(False)
     gemm_paths = dev.gemm_paths()
+    prof_steps = steps if graph is None else min(steps, 5)
     rank_ms = all_ranks(dist, ms / steps)
     ms = max_over_ranks(dist, ms)
     loss_value = float(loss.item())
@@ -394,6 +421,8 @@ def bench_mlp(dev, dist, rank, world, steps, warmup, peaks):
     barrier(dist)
     e2e_ms = max_over_ranks(dist, dev.elapsed_ms(f0, f1))
     wall_ms = (time.perf_counter() - t0) * 1e3
+    if graph is not None:
+        graph.close()
     if dp is not None:
         dp.close()
 
@@ -417,18 +446,20 @@ def bench_mlp(dev, dist, rank, world, steps, warmup, peaks):
         "clocks": clocks,
         "samples_per_s_per_sm_mhz": (GLOBAL_BATCH * steps / (ms * 1e-3)) / clocks["sm_mhz"] if clocks.get("sm_mhz") else None,
         "dp_parity": dp_parity,
+        "step_mode": ("cuda_graph_replay (md.capture_graph of the whole step incl. the NCCL exchange)" if graph is not None
+                      else "eager (one launch per op)" + (f"; graph capture failed: {graph_error}" if graph_error else "")),
         "roofline": tensor_roofline(
             gemm_tflops, peaks, kernel="mdb_gemm (matmul fwd + dW/dX gradient GEMMs): tc::gemm_3xtf32_pair_kernel",
             traffic=GEMM_TRAFFIC_BYTES_PER_LAUNCH if world == 1 else None,
             traffic_src=GEMM_TRAFFIC_SRC,
             algorithmic_bytes_per_launch=GEMM_ALGORITHMIC_BYTES_PER_LAUNCH if world == 1 else None,
             launches=int(gemm_n), avg_launch_ms=gemm_ms / gemm_n if gemm_n else None,
-            share_of_step=gemm_ms / ms if ms else None, gemm_paths=gemm_paths),
+            share_of_step=(gemm_ms / prof_steps) / (ms / steps) if ms else None, gemm_paths=gemm_paths),
         "other_kernels": {
-            "elementwise": {"ms_per_step": ew_ms / steps, "calls_per_step": ew_n / steps,
+            "elementwise": {"ms_per_step": ew_ms / prof_steps, "calls_per_step": ew_n / prof_steps,
                             "algorithmic_GBps": ew_bytes / (ew_ms * 1e-3) / 1e9 if ew_ms else None,
                             "frac_of_hbm": ew_bytes / (ew_ms * 1e-3) / 1e9 / peaks["hbm_gbs"] if ew_ms else None},
-            "reduce": {"ms_per_step": red_ms / steps, "calls_per_step": red_n / steps,
+            "reduce": {"ms_per_step": red_ms / prof_steps, "calls_per_step": red_n / prof_steps,
                        "algorithmic_GBps": red_bytes / (red_ms * 1e-3) / 1e9 if red_ms else None,
                        "frac_of_hbm": red_bytes / (red_ms * 1e-3) / 1e9 / peaks["hbm_gbs"] if red_ms else None},
         },
@@ -1008,6 +1039,8 @@ def main():
     ap.add_argument("--sample-rows", type=int, default=0, help="--impl reference: rows per step (0 = full batch)")
     ap.add_argument("--cpu-budget-s", type=float, default=900.0,
                     help="--impl reference: shrink the per-step sample if K+W full-batch steps would exceed this")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="run the timed C4 step as one CUDA-graph replay (auto: multi-GPU runs only)")
     ap.add_argument("--skip-extras", action="store_true", help="skip the C1/C2/C3/C5 single-GPU benchmarks")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline legs")
     args = ap.parse_args()
@@ -1023,7 +1056,8 @@ def main():
     sys.argv = sys.argv[:1]
     dev = Dev()
     dist = dist_setup(world)
-    line = bench_mlp(dev, dist, rank, world, args.steps, warmup, peaks)
+    use_graph = args.graph == "on" or (args.graph == "auto" and world > 1)
+    line = bench_mlp(dev, dist, rank, world, args.steps, warmup, peaks, use_graph)
     line["warmup"] = warmup
     if rank == 0 and world == 1:
         if not args.skip_extras:
