@@ -250,6 +250,8 @@ int mdb_comm_unique_id(void* id128, const char* nccl_lib_path);          /* rank
 int mdb_comm_init(int rank, int world, const void* id128, const char* nccl_lib_path);
 int mdb_comm_allreduce_f32(void* ptr, size_t count, int average);        /* on the comm stream,
                                                                             ordered after compute */
+/* n buffers averaged in ONE NCCL launch (ncclGroupStart/End): small gradients ride with large ones */
+int mdb_comm_allreduce_multi_f32(void* const* ptrs, const size_t* counts, int n, int average);
 int mdb_comm_wait(void);                          /* compute stream waits for the comm stream    */
 /* per-exchange completion: every mdb_comm_allreduce_f32 gets the next sequence number; the compute
  * stream can wait for ONE of them (update that parameter while later gradients are still in flight) */

@@ -115,6 +115,7 @@ _SIGS = {
     "mdb_comm_unique_id": (C.c_int, [C.c_void_p, C.c_char_p]),
     "mdb_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_char_p]),
     "mdb_comm_allreduce_f32": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int]),
+    "mdb_comm_allreduce_multi_f32": (C.c_int, [_P(C.c_void_p), _P(C.c_size_t), C.c_int, C.c_int]),
     "mdb_comm_wait": (C.c_int, []),
     "mdb_comm_last_seq": (C.c_uint64, []),
     "mdb_comm_wait_seq": (C.c_int, [C.c_uint64]),

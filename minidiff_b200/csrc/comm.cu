@@ -17,6 +17,7 @@ typedef int (*fn_GetUniqueId)(NcclUniqueId*);
 typedef int (*fn_CommInitRank)(ncclComm_t*, int, NcclUniqueId, int);
 typedef int (*fn_AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
 typedef int (*fn_CommDestroy)(ncclComm_t);
+typedef int (*fn_Group)(void);
 typedef const char* (*fn_GetErrorString)(int);
 
 static void* g_nccl = nullptr;
@@ -24,6 +25,7 @@ static fn_GetUniqueId p_GetUniqueId;
 static fn_CommInitRank p_CommInitRank;
 static fn_AllReduce p_AllReduce;
 static fn_CommDestroy p_CommDestroy;
+static fn_Group p_GroupStart, p_GroupEnd;
 static fn_GetErrorString p_GetErrorString;
 static ncclComm_t g_comm = nullptr;
 static cudaStream_t g_comm_stream = nullptr;
@@ -49,6 +51,9 @@ static int load_nccl(const char* path) {
   p_AllReduce = (fn_AllReduce)dlsym(g_nccl, "ncclAllReduce");
   p_CommDestroy = (fn_CommDestroy)dlsym(g_nccl, "ncclCommDestroy");
   p_GetErrorString = (fn_GetErrorString)dlsym(g_nccl, "ncclGetErrorString");
+  p_GroupStart = (fn_Group)dlsym(g_nccl, "ncclGroupStart");
+  p_GroupEnd = (fn_Group)dlsym(g_nccl, "ncclGroupEnd");
+  if (!p_GroupStart || !p_GroupEnd) return set_error(MDB_ECOMM, "libnccl is missing ncclGroupStart/End");
   if (!p_GetUniqueId || !p_CommInitRank || !p_AllReduce || !p_CommDestroy || !p_GetErrorString)
     return set_error(MDB_ECOMM, "libnccl is missing required symbols");
   return 0;
@@ -98,6 +103,29 @@ int mdb_comm_allreduce_f32(void* ptr, size_t count, int average) {
   const int ncclFloat32 = 7, ncclSum = 0, ncclAvg = 4;
   MDB_NCCL(p_AllReduce(ptr, ptr, count, ncclFloat32, average ? ncclAvg : ncclSum, g_comm,
                        g_comm_stream));
+  MDB_CUDA(cudaEventRecord(g_ev_comm, g_comm_stream));
+  ++g_seq;
+  MDB_CUDA(cudaEventRecord(g_ev_seq[g_seq % kSeqRing], g_comm_stream));
+  return 0;
+}
+
+// Several gradient buffers in ONE NCCL launch (ncclGroupStart/End fuses the calls into one kernel):
+// a bias gradient of a few KB rides with its layer's weight gradient instead of paying its own launch.
+int mdb_comm_allreduce_multi_f32(void* const* ptrs, const size_t* counts, int n, int average) {
+  MDB_REQUIRE(g_comm != nullptr, "communicator not initialised");
+  MDB_REQUIRE(n >= 1 && n <= 64 && ptrs && counts, "allreduce_multi: 1..64 buffers");
+  MDB_CUDA(cudaEventRecord(g_ev_compute, g_stream));
+  MDB_CUDA(cudaStreamWaitEvent(g_comm_stream, g_ev_compute, 0));
+  const int ncclFloat32 = 7, ncclSum = 0, ncclAvg = 4;
+  MDB_NCCL(p_GroupStart());
+  for (int i = 0; i < n; ++i) {
+    int r = p_AllReduce(ptrs[i], ptrs[i], counts[i], ncclFloat32, average ? ncclAvg : ncclSum, g_comm, g_comm_stream);
+    if (r != 0) {
+      p_GroupEnd();
+      return set_error(MDB_ECOMM, "ncclAllReduce (grouped) -> %s", p_GetErrorString(r));
+    }
+  }
+  MDB_NCCL(p_GroupEnd());
   MDB_CUDA(cudaEventRecord(g_ev_comm, g_comm_stream));
   ++g_seq;
   MDB_CUDA(cudaEventRecord(g_ev_seq[g_seq % kSeqRing], g_comm_stream));

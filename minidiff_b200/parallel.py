@@ -45,6 +45,7 @@ class DataParallel:
         self.overlap = overlap
         self._pending = False
         self._seq = {}
+        self._held = []
         self._flushed = False
         if self.world == 1:
             return
@@ -71,11 +72,19 @@ class DataParallel:
             for p in self.params:
                 p._grad_hook = self._on_grad_ready
 
+    SMALL = 1 << 16          # gradients below this many elements wait for the next large one
+
     # called by the backward sweep as soon as p.grad is final
     def _on_grad_ready(self, p):
-        self._allreduce(p)
+        """Bucketing without a flat arena: a small gradient (a bias: a few KB) is held back and rides
+        in the NCCL launch of the next large one (its layer's weight gradient, which the backward sweep
+        finishes right after) -- ncclGroupStart/End fuses the calls into one kernel, so the C4 step
+        issues 3 exchanges instead of 6."""
+        self._held.append(p)
+        if p.grad._data.size >= self.SMALL:
+            self._launch_held()
 
-    def _allreduce(self, p):
+    def _private_f32(self, p):
         g = p.grad._data
         # all-reduce IN PLACE only when this sweep provably owns the buffer (a fresh GEMM / reduction
         # output).  The engine aliases gradients like the reference does -- `a + b` hands the upstream
@@ -89,16 +98,36 @@ class DataParallel:
 
             p.grad = md.Tensor(F.astype(g, np.float32))
             g = p.grad._data
-        check(lib.mdb_comm_allreduce_f32(g.ptr, g.size, 1))
-        self._seq[id(p)] = int(lib.mdb_comm_last_seq())
+        return g
+
+    def _launch_held(self):
+        if not self._held:
+            return
+        bufs = [self._private_f32(p) for p in self._held]
+        n = len(bufs)
+        if n == 1:
+            check(lib.mdb_comm_allreduce_f32(bufs[0].ptr, bufs[0].size, 1))
+        else:
+            ptrs = (C.c_void_p * n)(*[b.ptr for b in bufs])
+            counts = (C.c_size_t * n)(*[b.size for b in bufs])
+            check(lib.mdb_comm_allreduce_multi_f32(ptrs, counts, n, 1))
+        seq = int(lib.mdb_comm_last_seq())
+        for p in self._held:
+            self._seq[id(p)] = seq
+        self._held = []
         self._pending = True
+
+    def _allreduce(self, p):
+        self._held.append(p)
+        self._launch_held()
 
     def flush(self):
         """Issue the exchanges that the backward hooks did not (overlap=False); no waiting."""
         if self.world > 1 and not self.overlap and not self._flushed:
-            for p in self.params:
-                self._allreduce(p)
+            self._held = list(self.params)
             self._flushed = True
+        if self.world > 1:
+            self._launch_held()          # small gradients still waiting for a large one
 
     def wait(self, p):
         """Order the compute stream after the exchange of THIS parameter's gradient only, so the

@@ -46,6 +46,17 @@ LAUNCH(mdb_elementwise, int op, const void* o, int n, const void* i)
 LAUNCH(mdb_reduce, int r, const void* o, const void* i, uint32_t m)
 LAUNCH(mdb_elementwise_reduce, int op, const void* o, int n, const void* i, int a)
 LAUNCH(mdb_gemm, const void* c, const void* a, const void* b, int acc)
+LAUNCH(mdb_gemm_batched, const void* c, const void* a, const void* b)
+LAUNCH(mdb_random_bits, const void* o, uint64_t s, uint64_t off)
+LAUNCH(mdb_randint, const void* o, int64_t lo, int64_t hi, uint64_t s, uint64_t off)
+LAUNCH(mdb_binomial, const void* o, int64_t n, const void* p, uint64_t s, uint64_t off)
+LAUNCH(mdb_permutation, const void* o, const void* b)
+LAUNCH(mdb_cumsum_f64, const void* o, const void* i)
+LAUNCH(mdb_searchsorted_cdf, const void* o, const void* c, const void* u)
+LAUNCH(mdb_index_offsets, const void* o, const void* i, int64_t e, int64_t s, int a)
+LAUNCH(mdb_unravel_index, const void* o, const void* i, int nd, const int64_t* d)
+LAUNCH(mdb_isin, const void* o, const void* e, const void* t, int inv)
+int mdb_nonzero(const void* m, const void* o, int64_t* c) { (void)m; (void)o; *c = 0; return 0; }
 LAUNCH(mdb_gemm_fused, const void* c, const void* a, const void* b, int acc, const void* bias, int relu, const void* m)
 LAUNCH(mdb_gather_rows, const void* o, const void* s, const void* i)
 LAUNCH(mdb_scatter_rows, const void* d, const void* s, const void* i, int add)
@@ -58,6 +69,7 @@ int mdb_gemm_last_plan(int* o) { memset(o, 0, 32); return 0; }
 int mdb_comm_unique_id(void* id, const char* p) { (void)id; (void)p; return 0; }
 int mdb_comm_init(int r, int w, const void* id, const char* p) { (void)r; (void)w; (void)id; (void)p; return 0; }
 int mdb_comm_allreduce_f32(void* p, size_t n, int avg) { (void)p; (void)n; (void)avg; return 0; }
+int mdb_comm_allreduce_multi_f32(void* const* p, const size_t* c, int n, int avg) { (void)p; (void)c; (void)n; (void)avg; return 0; }
 int mdb_comm_wait(void) { return 0; }
 uint64_t mdb_comm_last_seq(void) { return 0; }
 int mdb_comm_wait_seq(uint64_t s) { (void)s; return 0; }

@@ -54,12 +54,12 @@ else:
     # engine hands the upstream gradient buffer to both inputs of `+`, like the reference): the
     # exchange must not average that shared buffer in place while backward still reads it
     rng = np.random.default_rng(77)
-    Wa_np = rng.standard_normal((DIMS[0], 48)).astype(np.float32)
-    Pa_np = rng.standard_normal((BATCH // world, 48)).astype(np.float32)
+    Wa_np = rng.standard_normal((DIMS[0], 1024)).astype(np.float32)
+    Pa_np = rng.standard_normal((BATCH // world, 1024)).astype(np.float32)
     Wa, Pa = md.Tensor(Wa_np.copy(), allow_grad=True), md.Tensor(Pa_np.copy(), allow_grad=True)
     dp2 = DataParallel.__new__(DataParallel)          # second parameter set on the same communicator
     dp2.__dict__.update(dp.__dict__)
-    dp2.params, dp2._seq, dp2._pending, dp2._flushed = [Wa, Pa], {}, False, False
+    dp2.params, dp2._seq, dp2._pending, dp2._flushed, dp2._held = [Wa, Pa], {}, False, False, []
     for q in dp2.params:
         q._grad_hook = dp2._on_grad_ready
     alias = []

@@ -53,8 +53,8 @@ def test_two_gpu_step_matches_single_gpu(tmp_path):
         np.testing.assert_allclose(got[f"arr_{i}"], p.as_numpy(), rtol=1e-4, atol=1e-6)
     # aliased-gradient scenario of the worker: expected averages computed with NumPy per shard
     rng = np.random.default_rng(77)
-    Wa = rng.standard_normal((dims[0], 48)).astype(np.float32)
-    Pa = rng.standard_normal((batch // 2, 48)).astype(np.float32)
+    Wa = rng.standard_normal((dims[0], 1024)).astype(np.float32)
+    Pa = rng.standard_normal((batch // 2, 1024)).astype(np.float32)
     dW, dP = 0, 0
     for r_ in range(2):
         Xs = X[r_ * batch // 2:(r_ + 1) * batch // 2].astype(np.float64)
