@@ -153,6 +153,11 @@ int mdb_copy(const mdb_array* out, const mdb_array* in);
 /* every elementwise backend function; `out` may alias in[0] exactly (the `+=` family of
  * tensor.py:269-362).  Inputs broadcast against out's shape (stride 0 where stretched). */
 int mdb_elementwise(int op, const mdb_array* out, int n_in, const mdb_array* in);
+/* the same op with the operands passed as pointers to descriptors (what the shim's arrays cache) and
+ * an output that is ALLOCATED by the call when out->ptr is NULL (C-contiguous; the address is written
+ * back into out->ptr): one ABI crossing per backend function instead of alloc + marshal + launch */
+int mdb_elementwise_new(int op, mdb_array* out, int n_in, const mdb_array* in0, const mdb_array* in1,
+                        const mdb_array* in2);
 /* sum/mean/max/min/prod/any/all/argmax/argmin over the axes whose bit is set in axis_mask;
  * `out` is given in keepdims form (same ndim as `in`, reduced extents 1). */
 int mdb_reduce(int red, const mdb_array* out, const mdb_array* in, uint32_t axis_mask);

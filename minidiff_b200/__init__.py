@@ -14,6 +14,8 @@ from .tensor import Tensor, try_unwrap  # noqa: F401,E402
 from .topology import OpNode  # noqa: F401,E402
 from .ops.wrapping import *  # noqa: F401,F403,E402
 from .ops.definitions import *  # noqa: F401,F403,E402
+from .tensor import _install_operators as _install_operators  # noqa: E402
+_install_operators(resolve=True)      # operator dunders call the op functions directly from here on
 from .caching import reuse_graph  # noqa: F401,E402
 from .graphs import CapturedGraph, capture_graph  # noqa: F401,E402
 from .ops.fused_ops import make_ops as _make_fused_ops  # noqa: E402

@@ -89,6 +89,7 @@ _SIGS = {
     "mdb_fill": (C.c_int, [_A, C.c_double]),
     "mdb_copy": (C.c_int, [_A, _A]),
     "mdb_elementwise": (C.c_int, [C.c_int, _A, C.c_int, _A]),
+    "mdb_elementwise_new": (C.c_int, [C.c_int, _A, C.c_int, _A, _A, _A]),
     "mdb_reduce": (C.c_int, [C.c_int, _A, _A, C.c_uint32]),
     "mdb_elementwise_reduce": (C.c_int, [C.c_int, _A, C.c_int, _A, C.c_int]),
     "mdb_gemm": (C.c_int, [_A, _A, _A, C.c_int]),

@@ -46,11 +46,13 @@ class _Storage:
 
     __slots__ = ("ptr", "nbytes", "__weakref__")
 
-    def __init__(self, nbytes: int):
-        _lib.ensure_device()
-        p = C.c_void_p()
-        check(lib.mdb_alloc(max(int(nbytes), 1), C.byref(p)))
-        self.ptr = p.value
+    def __init__(self, nbytes: int, ptr=None):
+        if ptr is None:
+            _lib.ensure_device()
+            p = C.c_void_p()
+            check(lib.mdb_alloc(max(int(nbytes), 1), C.byref(p)))
+            ptr = p.value
+        self.ptr = ptr          # adopted: allocated by the library inside mdb_elementwise_new
         self.nbytes = nbytes
 
     def __del__(self, _free=lib.mdb_free):
@@ -92,6 +94,22 @@ class DeviceArray:
         dtype_code(dtype)
         st = _Storage(math.prod(shape) * dtype.itemsize)
         return cls(st, st.ptr, shape, c_strides(shape), dtype)
+
+    @classmethod
+    def _adopt(cls, desc, shape, estrides, dtype, size) -> "DeviceArray":
+        """Wrap an output the library allocated itself (mdb_elementwise_new filled desc.ptr); the
+        descriptor becomes the array's cached one.  Hot path: no argument normalisation."""
+        ptr = desc.ptr
+        self = cls.__new__(cls)
+        self._st = _Storage(size * dtype.itemsize, ptr)
+        self.ptr = ptr
+        self.shape = shape
+        self.estrides = estrides
+        self.dtype = dtype
+        self.writeable = True
+        self._desc = desc
+        self.size = size
+        return self
 
     @classmethod
     def from_numpy(cls, a) -> "DeviceArray":

@@ -68,6 +68,17 @@ def _dtype_token(x):
 
 def result_dtype(*xs):
     first = xs[0]
+    if len(xs) == 2 and first.__class__ is DeviceArray:       # the two commonest cases, decided at once
+        second = xs[1]
+        c = second.__class__
+        if c is DeviceArray:
+            if second.dtype is first.dtype:
+                return first.dtype
+        elif c is float:
+            if first.dtype.kind == "f":
+                return first.dtype
+        elif c is int and first.dtype.kind in "iuf":
+            return first.dtype
     if isinstance(first, DeviceArray):
         dt = first.dtype
         for x in xs[1:]:
@@ -131,7 +142,109 @@ def _launch_ew(op: str, out: DeviceArray, operands) -> DeviceArray:
     return out
 
 
+# ---- hot path of every elementwise backend function -------------------------------------------------
+# What repeats from call to call is cached per (op, output dtype, operand shapes): the broadcast shape,
+# the output strides and a byte image of the output descriptor.  A call then costs one descriptor copy,
+# immediates written into three scratch descriptors, ONE ABI crossing (mdb_elementwise_new allocates the
+# output and launches) and the DeviceArray that adopts the result.  Anything unusual (NumPy scalars,
+# host data, all-scalar calls, > 3 operands) takes the general path below.
+_PLANS: dict = {}
+_IMM_DESC = [MdbArray() for _ in range(3)]
+_IMM_REF = [_byref(d) for d in _IMM_DESC]
+_F64_CODE, _I64_CODE = _lib.F64, _lib.I64
+_new_call = lib.mdb_elementwise_new
+_desc_from = MdbArray.from_buffer_copy
+
+
+def _make_plan(key, op, out_dtype, shapes):
+    shape = broadcast_shapes([s for s in shapes if s is not None])
+    if len(shape) > _lib.MAX_DIMS:
+        raise ValueError(f"at most {_lib.MAX_DIMS} dimensions are supported")
+    strides = c_strides(shape)
+    d = MdbArray()
+    d.ptr = None
+    d.dtype = dtype_code(out_dtype)
+    d.ndim = len(shape)
+    for i, (e, st) in enumerate(zip(shape, strides)):
+        d.shape[i] = e
+        d.strides[i] = st
+    plan = (OP[op], shape, strides, math.prod(shape), bytes(d))
+    if len(_PLANS) > 4096:
+        _PLANS.clear()
+    _PLANS[key] = plan
+    return plan
+
+
+def _imm_ref(slot, v):
+    d = _IMM_DESC[slot]
+    if v.__class__ is float:
+        d.dtype = _F64_CODE
+        d.imm = v
+        d.imm_i = int(v) if (v == v and -9e18 < v < 9e18) else 0
+    else:
+        d.dtype = _I64_CODE
+        d.imm = v
+        d.imm_i = v
+    return _IMM_REF[slot]
+
+
+def _ew_into(op: str, out: DeviceArray, operands) -> bool:
+    """`out = op(*operands)` into an existing array through the one-crossing entry point; operands
+    are DeviceArrays or plain Python scalars that broadcast against out (the caller guarantees it).
+    Returns False when an operand needs the general path."""
+    n = len(operands)
+    if n > 3:
+        return False
+    refs = [None, None, None]
+    for i, o in enumerate(operands):
+        c = o.__class__
+        if c is DeviceArray:
+            dd = o._desc
+            refs[i] = _byref(dd if dd is not None else o.d)
+        elif (c is float or c is int) and -9.2e18 < o < 9.2e18:
+            refs[i] = _imm_ref(i, o)
+        else:
+            return False
+    dd = out._desc
+    rc = _new_call(OP[op], dd if dd is not None else out.d, n, refs[0], refs[1], refs[2])
+    if rc:
+        check(rc)
+    return True
+
+
 def _ew(op: str, out_dtype, *operands) -> DeviceArray:
+    n = len(operands)
+    if n <= 3:
+        shapes = []
+        fast = False
+        for o in operands:
+            c = o.__class__
+            if c is DeviceArray:
+                shapes.append(o.shape)
+                fast = True
+            elif (c is float or c is int) and -9.2e18 < o < 9.2e18 or c is bool:
+                shapes.append(None)
+            else:
+                fast = False
+                break
+        if fast:
+            key = (op, out_dtype, *shapes)
+            plan = _PLANS.get(key)
+            if plan is None:
+                plan = _make_plan(key, op, np.dtype(out_dtype), shapes)
+            opid, shape, strides, size, image = plan
+            d = _desc_from(image)
+            refs = [None, None, None]
+            for i, o in enumerate(operands):
+                if o.__class__ is DeviceArray:
+                    dd = o._desc
+                    refs[i] = _byref(dd if dd is not None else o.d)
+                else:
+                    refs[i] = _imm_ref(i, int(o) if o.__class__ is bool else o)
+            rc = _new_call(opid, d, n, refs[0], refs[1], refs[2])
+            if rc:
+                check(rc)
+            return DeviceArray._adopt(d, shape, strides, out_dtype if out_dtype.__class__ is np.dtype else np.dtype(out_dtype), size)
     operands = [_operand(o) for o in operands]
     shape = broadcast_shapes([o.shape for o in operands if isinstance(o, DeviceArray)] or [()])
     if not any(isinstance(o, DeviceArray) for o in operands):
@@ -176,6 +289,8 @@ def elementwise_into(op: str, out: DeviceArray, *operands) -> DeviceArray:
     if shape != out.shape and broadcast_shapes([shape, out.shape]) != out.shape:
         raise ValueError(f"non-broadcastable output operand with shape {out.shape} doesn't match "
                          f"the broadcast shape {shape}")
+    if _ew_into(op, out, operands):
+        return out
     return _launch_ew(op, out, operands)
 
 
@@ -223,7 +338,11 @@ def _unary_same(op):
 
 def _binary_arith(op, name):
     def f(x, y, **_kw):
-        x, y = _operand(x), _operand(y)
+        cx, cy = x.__class__, y.__class__
+        if not (cx is DeviceArray or cx is float or cx is int):
+            x = _operand(x)
+        if not (cy is DeviceArray or cy is float or cy is int):
+            y = _operand(y)
         return _ew(op, result_dtype(x, y), x, y)
 
     f.__name__ = name

@@ -595,6 +595,36 @@ int mdb_elementwise(int op, const mdb_array* out, int n_in, const mdb_array* in)
   return mdb::elementwise_impl(op, out, n_in, in);
 }
 
+// One call per op for the host shim: the operands come as POINTERS to the descriptors the arrays
+// already cache (no descriptor array to marshal), and an output whose ptr is NULL is allocated here
+// from the caching allocator (contiguous, numel * itemsize bytes) and its address written back --
+// alloc + launch in one ABI crossing instead of two.
+int mdb_elementwise_new(int op, mdb_array* out, int n_in, const mdb_array* in0, const mdb_array* in1,
+                        const mdb_array* in2) {
+  MDB_REQUIRE(n_in >= 1 && n_in <= 3 && out && in0 && (n_in < 2 || in1) && (n_in < 3 || in2),
+              "elementwise takes 1..3 inputs, got %d", n_in);
+  mdb_array in[3];
+  in[0] = *in0;
+  if (n_in > 1) in[1] = *in1;
+  if (n_in > 2) in[2] = *in2;
+  bool fresh = false;
+  if (!out->ptr) {
+    int64_t n = 1;
+    for (int d = 0; d < out->ndim; ++d) n *= out->shape[d];
+    void* p = nullptr;
+    MDB_TRY(mdb_alloc((size_t)(n > 0 ? n : 1) * (size_t)mdb::dtype_size(out->dtype), &p));
+    out->ptr = p;
+    fresh = true;
+  }
+  int rc;
+  {
+    mdb::ProfScope prof(mdb::PROF_ELEMENTWISE, mdb::algorithmic_bytes(out, n_in, in));
+    rc = mdb::elementwise_impl(op, out, n_in, in);
+  }
+  if (rc != 0 && fresh) { mdb_free(out->ptr); out->ptr = nullptr; }
+  return rc;
+}
+
 int mdb_copy(const mdb_array* out, const mdb_array* in) {
   mdb::ProfScope prof(mdb::PROF_ELEMENTWISE, mdb::algorithmic_bytes(out, 1, in));
   return mdb::elementwise_impl(MDB_OP_COPY, out, 1, in);

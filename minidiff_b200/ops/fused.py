@@ -51,20 +51,38 @@ def _reduces_to(shape, tshape) -> bool:
 
 def contribute(target, op: str, *operands) -> bool:
     """target.grad (+)= unbroadcast(op(*operands), target.shape), one launch."""
-    if target._data.dtype != F32 or not all(_ok_operand(o) for o in operands):
+    tdata = target._data
+    if tdata.dtype != F32:
         return False
-    arrays = [o for o in operands if isinstance(o, DeviceArray)]
-    if not any(a.dtype == F32 for a in arrays):
+    shape, any_f32, same = None, False, True
+    for o in operands:
+        c = o.__class__
+        if c is DeviceArray:
+            dt = o.dtype
+            if dt == F32:
+                any_f32 = True
+            elif dt != BOOL:
+                return False
+            if shape is None:
+                shape = o.shape
+            elif o.shape != shape:
+                same = False
+        elif not ((c is int or c is float)):
+            if not _ok_operand(o):
+                return False
+    if not any_f32:
         return False
-    shape = F.broadcast_shapes([a.shape for a in arrays])
-    tshape = target._data.shape
+    if not same:
+        shape = F.broadcast_shapes([o.shape for o in operands if o.__class__ is DeviceArray])
+    tshape = tdata.shape
     dst = OpNode.private_grad_buffer(target)
     if shape == tshape:
         if dst is not None and op == "MUL":
-            F._launch_ew("FMA", dst, [dst, *operands])        # dst = dst + a*b, in place
+            if not F._ew_into("FMA", dst, (dst, *operands)):          # dst = dst + a*b, in place
+                F._launch_ew("FMA", dst, [dst, *operands])
             return True
-        fresh = F._launch_ew(op, DeviceArray.empty(shape, F32), list(operands))
-        OpNode.accumulate(target, md.Tensor(fresh), private=True)
+        fresh = F._ew(op, F32, *operands)
+        OpNode.accumulate(target, md.Tensor._wrap(fresh), private=True)
         return True
     if not _reduces_to(shape, tshape):
         return False
@@ -78,7 +96,7 @@ def contribute(target, op: str, *operands) -> bool:
             F._fill_imm(descs[i], o)
     check(lib.mdb_elementwise_reduce(OP[op], C.byref(out.d), n, descs, 1 if dst is not None else 0))
     if dst is None:
-        OpNode.accumulate(target, md.Tensor(out), private=True)
+        OpNode.accumulate(target, md.Tensor._wrap(out), private=True)
     return True
 
 

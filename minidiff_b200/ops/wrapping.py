@@ -65,17 +65,32 @@ class TernaryOpClass(OpClass):
     pass
 
 
+_CONTAINERS = (tuple, list, dict)
+
+
+def _unwrap_args(args):
+    """try_unwrap over positional arguments, without the generic recursion for the common case
+    (Tensors and plain scalars)."""
+    Tensor, unwrap = md.Tensor, md.try_unwrap
+    return [a._data if a.__class__ is Tensor else (unwrap(a) if isinstance(a, _CONTAINERS) or isinstance(a, Tensor) else a)
+            for a in args]
+
+
 def as_minidiff(func):
     """Raw-array function -> Tensor function (wrapping.py:117-134): unwrap Tensors in args and
     kwargs, make ONE backend call (== one kernel launch on the compute stream), wrap the result."""
 
     def wrapper(*args, **kwargs):
         allow_grad = _tracks_grad(args)
-        out = func(*md.try_unwrap(args), **md.try_unwrap(kwargs))
+        if kwargs:
+            out = func(*_unwrap_args(args), **md.try_unwrap(kwargs))
+        else:
+            out = func(*_unwrap_args(args))
         return md.Tensor(out, allow_grad=allow_grad)
 
     wrapper.__name__ = func.__name__
     wrapper.__qualname__ = getattr(func, "__qualname__", func.__name__)
+    wrapper._mdb_raw = func          # create_op_func calls the backend function directly (one wrap, not two)
     return wrapper
 
 
@@ -96,7 +111,39 @@ def create_op_func(forward_func, grad_funcs, propagate_kwargs=False, is_differen
     if op_name is None:
         op_name = forward_func.__name__
 
+    raw = getattr(forward_func, "_mdb_raw", None)
+    grad_mode = md.grad_allowed_
+
     def minidiff_func(*op_inputs, **op_kwargs):
+        if raw is not None:
+            # forward_func is as_minidiff(raw).  Same checks and results as the general path below, done
+            # in ONE pass over the inputs: validation (wrapping.py:28-44), the allow_grad decision
+            # (wrapping.py:17-25) and the unwrapping, then one backend call and one Tensor.
+            Tensor = md.Tensor
+            args, ok, tracks = [], False, False
+            decided = False
+            for a in op_inputs:
+                if a.__class__ is Tensor or isinstance(a, Tensor):
+                    args.append(a._data)
+                    if a._allow_grad:
+                        tracks = True
+                    is_t = True
+                else:
+                    args.append(md.try_unwrap(a) if isinstance(a, _CONTAINERS) else a)
+                    is_t = False
+                if not decided:
+                    ok = is_t
+                    decided = is_t != tensor_only
+            if not ok:
+                raise ValueError("This function only supports minidiff Tensors" if tensor_only else
+                                 "This function requires at least one minidiff Tensor argument")
+            allow_grad = tracks and grad_mode()
+            out = raw(*args, **md.try_unwrap(op_kwargs)) if op_kwargs else raw(*args)
+            output = Tensor._wrap(out, allow_grad) if out.__class__ is Tensor._raw_class else Tensor(out, allow_grad=allow_grad)
+            if is_differentiable and allow_grad:
+                output.op_node = OpNode(forward_func, grad_funcs, op_inputs, op_kwargs, op_name,
+                                        propagate_kwargs, fused_backward)
+            return output
         _check_inputs(op_inputs, tensor_only)
         allow_grad = _tracks_grad(op_inputs)
         output = forward_func(*op_inputs, **op_kwargs)

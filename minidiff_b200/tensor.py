@@ -88,6 +88,7 @@ class Tensor:
     __slots__ = ("_data", "_allow_grad", "_iterator", "graph_refs", "grad", "op_node",
                  "_grad_private", "_grad_hook", "__weakref__")
     __array_ufunc__ = None  # numpy scalars defer to our reflected operators
+    _raw_class = DeviceArray
 
     def __init__(self, data, allow_grad=False, dtype=None):
         data = try_unwrap(data)
@@ -109,6 +110,20 @@ class Tensor:
         # optional callable(tensor) fired by the backward sweep once this leaf's gradient is
         # complete (used by parallel.DataParallel to start the all-reduce early)
         self._grad_hook = None
+
+    @classmethod
+    def _wrap(cls, data, allow_grad=False):
+        """Tensor around a raw DeviceArray without argument normalisation (the per-op hot path)."""
+        self = cls.__new__(cls)
+        self._data = data
+        self._allow_grad = allow_grad
+        self._iterator = None
+        self.graph_refs = 0
+        self.grad = None
+        self.op_node = None
+        self._grad_private = None
+        self._grad_hook = None
+        return self
 
     # ---- graph flags (tensor.py:115-148)
     @property
@@ -228,17 +243,26 @@ class Tensor:
         return backend.array(self._data, dtype=dtype, copy=copy)
 
 
-def _install_operators():
+def _install_operators(resolve=False):
     """Operator overloads route to ops; augmented assignments mutate storage directly with one
-    in-place kernel (reference tensor.py:266-412)."""
+    in-place kernel (reference tensor.py:266-412).  Installed twice: while this module loads the op
+    table does not exist yet (per-call lookup through the package, like the reference); the package
+    __init__ re-installs them with the op functions resolved once."""
+    if not resolve:
+        class _Late:                      # getattr(md, name) at call time
+            def __init__(self, name): self.name = name
+            def __call__(self, *a): return getattr(md, self.name)(*a)
+        lookup = _Late
+    else:
+        lookup = lambda name: getattr(md, name)  # noqa: E731
     binary = {"add": "add", "sub": "subtract", "mul": "multiply", "truediv": "true_divide",
               "floordiv": "floor_divide", "pow": "power", "mod": "mod", "matmul": "matmul"}
     for dunder, op in binary.items():
-        def fwd(self, other, _op=op):
-            return getattr(md, _op)(self, other)
+        def fwd(self, other, _op=lookup(op)):
+            return _op(self, other)
 
-        def rev(self, other, _op=op):
-            return getattr(md, _op)(other, self)
+        def rev(self, other, _op=lookup(op)):
+            return _op(other, self)
 
         setattr(Tensor, f"__{dunder}__", fwd)
         if dunder not in ("mod", "matmul"):
@@ -247,8 +271,8 @@ def _install_operators():
                "eq": "equal", "ne": "not_equal", "and": "logical_and", "or": "logical_or",
                "xor": "logical_xor"}
     for dunder, op in compare.items():
-        def cmp(self, value, _op=op):
-            return getattr(md, _op)(self, value)
+        def cmp(self, value, _op=lookup(op)):
+            return _op(self, value)
 
         setattr(Tensor, f"__{dunder}__", cmp)
     for dunder in ("iadd", "isub", "imul", "itruediv", "ifloordiv", "ipow", "imod"):

@@ -33,8 +33,9 @@ class OpNode:
         self.op_name = "" if op_name is None else op_name
         self.propagate_kwargs = propagate_kwargs
         self.fused_backward = fused_backward
-        self.tensor_inputs = [x for x in op_inputs if isinstance(x, md.Tensor)]
-        for t in self.tensor_inputs:
+        Tensor = md.Tensor
+        self.tensor_inputs = tensors = [x for x in op_inputs if x.__class__ is Tensor or isinstance(x, Tensor)]
+        for t in tensors:
             t.graph_refs += 1
         self._tensor_graph = []
         if not mdc.currently_caching():
@@ -98,24 +99,28 @@ class OpNode:
     # ------------------------------------------------------------------ ordering
     def toposort(self):
         """Tensors below this node in dependency order (inputs before consumers), each once
-        (same order as the reference's recursive DFS, topology.py:106-128)."""
+        (same order as the reference's recursive DFS, topology.py:106-128): iterative post-order
+        with one iterator per open node, so graph depth is not bounded by the recursion limit."""
         order, seen = [], set()
-        stack = [(self, 0)]
+        add_seen, emit = seen.add, order.append
+        stack = [(None, iter(self.tensor_inputs))]
         while stack:
-            node, i = stack.pop()
-            if isinstance(node, md.Tensor):
-                order.append(node)
-                continue
-            if i >= len(node.tensor_inputs):
-                continue
-            stack.append((node, i + 1))
-            t = node.tensor_inputs[i]
-            if id(t) in seen:
-                continue
-            seen.add(id(t))
-            stack.append((t, 0))
-            if t.op_node is not None:
-                stack.append((t.op_node, 0))
+            tensor, it = stack[-1]
+            for child in it:
+                cid = id(child)
+                if cid in seen:
+                    continue
+                add_seen(cid)
+                node = child.op_node
+                if node is None:
+                    emit(child)                       # leaf: nothing below it
+                else:
+                    stack.append((child, iter(node.tensor_inputs)))
+                    break
+            else:
+                stack.pop()
+                if tensor is not None:
+                    emit(tensor)
         return order
 
     # ------------------------------------------------------------------ reverse sweep
