@@ -244,7 +244,7 @@ def _ew(op: str, out_dtype, *operands) -> DeviceArray:
             rc = _new_call(opid, d, n, refs[0], refs[1], refs[2])
             if rc:
                 check(rc)
-            return DeviceArray._adopt(d, shape, strides, out_dtype if out_dtype.__class__ is np.dtype else np.dtype(out_dtype), size)
+            return DeviceArray._adopt(d, shape, strides, out_dtype if isinstance(out_dtype, np.dtype) else np.dtype(out_dtype), size)
     operands = [_operand(o) for o in operands]
     shape = broadcast_shapes([o.shape for o in operands if isinstance(o, DeviceArray)] or [()])
     if not any(isinstance(o, DeviceArray) for o in operands):
