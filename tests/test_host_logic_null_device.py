@@ -94,7 +94,7 @@ def test_host_logic_launch_counts_shapes_and_errors():
     # reference chain: 8 forward + 14 backward calls; fused backward here: seed + 5 fused gradient launches
     # (at 8192 x 8192 the column sum splits its rows and adds one fold launch: 12 per iteration)
     assert got["c2_forward"] == 5 and got["c2_backward_fused"] == 6
-    assert got["c4_step"] == 41
+    assert got["c4_step"] == 38       # 41 at batch 65536: the three bias-gradient column sums add a fold launch each
     assert got["c4_fused_fwd_bwd"] <= 20
     assert got["c1_meta"] == [[2, 4], "float32", [2, 4], "float32"]
     assert got["c2_meta"] == [[], [64, 1], [1, 48]]
