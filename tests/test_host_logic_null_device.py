@@ -57,7 +57,7 @@ meta["flip"] = list(B.flip(B.zeros((4, 6), dtype=np.float32), 1).strides)
 meta["matmul"] = [list(B.matmul(B.zeros((7, 3), dtype=np.float32), B.zeros((3, 2), dtype=np.float32)).shape),
                   list(B.matmul(B.zeros((5, 7, 3)), B.zeros((3, 2))).shape), str(B.matmul(B.zeros((2, 2), dtype=np.int64), B.zeros((2, 2), dtype=np.int64)).dtype)]
 errs = {}
-for name, fn in (("bcast", lambda: t + B.zeros((2, 5), dtype=np.float32)), ("matmul", lambda: B.matmul(B.zeros((2, 3)), B.zeros((4, 2)))),
+for name, fn in (("bcast", lambda: t + B.zeros((2, 4), dtype=np.float32)), ("matmul", lambda: B.matmul(B.zeros((2, 3)), B.zeros((4, 2)))),
                  ("readonly", lambda: B.broadcast_to(t, (2, 3, 1, 5)).__iadd__(1)), ("axis", lambda: B.sum(t, axis=3)),
                  ("index", lambda: t[5]), ("cast", lambda: B.zeros((2,), dtype=np.int64).__iadd__(1.5))):
     try:
