@@ -246,6 +246,8 @@ int mdb_randint(const mdb_array* out, int64_t low, int64_t high, uint64_t seed, 
 int mdb_binomial(const mdb_array* out, int64_t trials, const mdb_array* p, uint64_t seed, uint64_t offset);
 /* out = uniformly random permutation of 0..n-1 (device bitonic sort of (random word, i) keys) */
 int mdb_permutation(const mdb_array* out, const mdb_array* bits);
+/* arange (backend/numpy.py:127): out[i] = start + i*step; integral != 0 computes in int64 exactly */
+int mdb_arange(const mdb_array* out, double start, double step, int64_t istart, int64_t istep, int integral);
 /* weighted choice: inclusive float64 scan of the weights, then out[i] = searchsorted(cdf / cdf[-1], u[i], "right") */
 int mdb_cumsum_f64(const mdb_array* out, const mdb_array* in);
 int mdb_searchsorted_cdf(const mdb_array* out, const mdb_array* cdf, const mdb_array* u);

@@ -107,6 +107,7 @@ _SIGS = {
     "mdb_randint": (C.c_int, [_A, C.c_int64, C.c_int64, C.c_uint64, C.c_uint64]),
     "mdb_binomial": (C.c_int, [_A, C.c_int64, _A, C.c_uint64, C.c_uint64]),
     "mdb_permutation": (C.c_int, [_A, _A]),
+    "mdb_arange": (C.c_int, [_A, C.c_double, C.c_double, C.c_int64, C.c_int64, C.c_int]),
     "mdb_cumsum_f64": (C.c_int, [_A, _A]),
     "mdb_searchsorted_cdf": (C.c_int, [_A, _A, _A]),
     "mdb_index_offsets": (C.c_int, [_A, _A, C.c_int64, C.c_int64, C.c_int]),

@@ -27,6 +27,9 @@ def asarray(x, dtype=None) -> DeviceArray:
     if isinstance(x, DeviceArray):
         return x if dtype is None or np.dtype(dtype) == x.dtype else astype(x, dtype)
     if isinstance(x, (list, tuple)) and _contains_device(x):
+        if x and all(isinstance(e, DeviceArray) and e.shape == x[0].shape for e in x):
+            r = stack(list(x))                       # a list of device arrays: stacked on the device
+            return r if dtype is None or np.dtype(dtype) == r.dtype else astype(r, dtype)
         x = _to_host_nested(x)
     a = np.asarray(x) if dtype is None else np.asarray(x, dtype=dtype)
     return DeviceArray.from_numpy(a)
@@ -1117,8 +1120,24 @@ def ones_like(a, dtype=None, **_kw): return full_like(a, 1, dtype)
 
 
 def arange(*args, dtype=None, **_kw):
+    """np.arange semantics (length, dtype) decided on the host from the scalars, values written by one
+    kernel (C ABI mdb_arange): no host array is built."""
     args = [x.item() if isinstance(x, DeviceArray) else x for x in args]
-    return DeviceArray.from_numpy(np.arange(*args, dtype=dtype))  # index data staged from the host
+    if not 1 <= len(args) <= 3:
+        raise TypeError("arange() requires 1 to 3 positional arguments")
+    start, stop, step = (0, args[0], 1) if len(args) == 1 else (args[0], args[1], args[2] if len(args) == 3 else 1)
+    if step == 0:
+        raise ZeroDivisionError("division by zero")
+    dt = np.dtype(dtype) if dtype is not None else np.result_type(*[type(v) if isinstance(v, _pyscalar) else v for v in (start, stop, step)])
+    if dt == np.bool_ or dt.kind not in "iuf":
+        return DeviceArray.from_numpy(np.arange(*args, dtype=dtype))       # exotic dtypes: NumPy decides
+    n = max(0, int(math.ceil((stop - start) / step)))
+    out = DeviceArray.empty((n,), dt)
+    integral = dt.kind in "iu" and all(isinstance(v, (int, np.integer)) for v in (start, step))
+    if n:
+        check(lib.mdb_arange(_byref(out.d), float(start), float(step), int(start) if integral else 0,
+                             int(step) if integral else 0, 1 if integral else 0))
+    return out
 
 
 def concatenate(arrays, axis=0, **_kw):

@@ -297,6 +297,16 @@ __global__ void __launch_bounds__(256) searchsorted_kernel(const double* cdf, in
   out[i] = lo < m ? lo : m - 1;
 }
 
+// arange: out[i] = start + i * step (float64 arithmetic for float outputs like NumPy, exact int64 for ints)
+__global__ void __launch_bounds__(256) arange_kernel(void* out, int dtype, int64_t n, double start, double step,
+                                                     long long istart, long long istep, int integral) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (integral) store_as<long long>(out, dtype, i, istart + (long long)i * istep);
+    else store_as<double>(out, dtype, i, start + (double)i * step);
+  }
+}
+
 static bool is_contig(const mdb_array* a) {
   int64_t st = 1;
   for (int d = a->ndim - 1; d >= 0; --d) {
@@ -439,6 +449,16 @@ int mdb_permutation(const mdb_array* out, const mdb_array* bits) {
     MDB_CHECK_LAUNCH();
   }
   perm_extract_kernel<<<(unsigned)((n + 255) / 256), 256, 0, g_stream>>>(k, (long long*)out->ptr, n);
+  MDB_CHECK_LAUNCH();
+  return 0;
+}
+
+int mdb_arange(const mdb_array* out, double start, double step, int64_t istart, int64_t istep, int integral) {
+  MDB_TRY(ensure_init());
+  MDB_REQUIRE(out && out->ptr && is_contig(out), "arange: contiguous output required");
+  const int64_t n = numel(out);
+  if (n == 0) return 0;
+  arange_kernel<<<grid_for(n, 256), 256, 0, g_stream>>>(out->ptr, out->dtype, n, start, step, istart, istep, integral);
   MDB_CHECK_LAUNCH();
   return 0;
 }

@@ -57,6 +57,7 @@ LAUNCH(mdb_random_bits, const void* o, uint64_t s, uint64_t off)
 LAUNCH(mdb_randint, const void* o, int64_t lo, int64_t hi, uint64_t s, uint64_t off)
 LAUNCH(mdb_binomial, const void* o, int64_t n, const void* p, uint64_t s, uint64_t off)
 LAUNCH(mdb_permutation, const void* o, const void* b)
+LAUNCH(mdb_arange, const void* o, double a, double b, int64_t c, int64_t d, int e)
 LAUNCH(mdb_cumsum_f64, const void* o, const void* i)
 LAUNCH(mdb_searchsorted_cdf, const void* o, const void* c, const void* u)
 LAUNCH(mdb_index_offsets, const void* o, const void* i, int64_t e, int64_t s, int a)

@@ -308,3 +308,16 @@ def test_inplace_ops_on_overlapping_views_match_numpy(B):
     s += s                                      # exact aliasing stays ONE in-place launch
     assert launches() - l0 == 1
     np.testing.assert_array_equal(s.numpy(), a_np + a_np)
+
+
+def test_arange_and_stacking_stay_on_the_device(B):
+    for args, kw in (((10,), {}), ((2, 11), {}), ((0, 20, 3), {}), ((5, -5, -2), {}), ((0.0, 1.0, 0.125), {}),
+                     ((3,), {"dtype": np.float32}), ((7, 2), {}), ((0, 2**40, 2**37), {})):
+        got, want = B.arange(*args, **kw), np.arange(*args, **kw)
+        assert got.dtype == want.dtype and got.shape == want.shape, (args, got.dtype, want.dtype)
+        np.testing.assert_array_equal(got.numpy(), want)
+    rows = [B.asarray(np.full((3,), i, np.float32)) for i in range(4)]
+    l0 = launches()
+    s = B.asarray(rows)
+    assert s.shape == (4, 3) and launches() - l0 == 4          # one copy per row, nothing staged through the host
+    np.testing.assert_array_equal(s.numpy(), np.stack([r.numpy() for r in rows]))
