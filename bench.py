@@ -62,7 +62,7 @@ GEMM_TRAFFIC_SRC = ("dram__bytes_read.sum + dram__bytes_write.sum averaged over 
 C3_TRAFFIC_BYTES_PER_LAUNCH = 3.129e9
 C3_TRAFFIC_SRC = ("dram__bytes_read.sum + dram__bytes_write.sum per 8192^3 launch of the shipped pair kernel "
                   "(ncu --set full, profiles/r02_ncu_c3_gemm.md)")
-GLOBAL_BATCH = 65536
+GLOBAL_BATCH = int(os.environ.get("MDB_BENCH_GLOBAL_BATCH", 65536))   # override for experiments only (scripts/dp_contention.sh)
 DIMS = (1024, 4096, 4096, 1024)
 LR = 0.01
 METRIC = "mlp_train_samples_per_s"
@@ -334,6 +334,8 @@ def bench_mlp(dev, dist, rank, world, steps, warmup, peaks, use_graph=False):
     params = [md.Tensor(p, allow_grad=True) for p in W.mlp_params(DIMS)]
     X, Y = md.Tensor(X_np), md.Tensor(Y_np)
     dp = DataParallel(params, rank, world) if world > 1 else None
+    if os.environ.get("MDB_BENCH_GEMM_MAX_CLUSTERS"):          # experiment: leave SMs to the NCCL kernels
+        dev.check(dev.lib.mdb_gemm_knob(7, int(os.environ["MDB_BENCH_GEMM_MAX_CLUSTERS"])))
     dp_parity = dp_parity_check(dev, dist, rank, world, dp, X, Y, params, local) if world > 1 else None
 
     def eager_step():

@@ -191,7 +191,8 @@ int mdb_gemm_stats(uint64_t* counts, int reset);
 /* measurement knobs of the CTA-pair kernel's planner (-1 = automatic): tile order, L2 eviction hints
  * (0 none, 1 evict_first, 2 evict_last), stream-K (0 never, 1 whenever legal) */
 enum { MDB_GEMM_KNOB_RASTER = 0, MDB_GEMM_KNOB_GROUP = 1, MDB_GEMM_KNOB_HINT_A = 2, MDB_GEMM_KNOB_HINT_B = 3,
-       MDB_GEMM_KNOB_HINT_C = 4, MDB_GEMM_KNOB_STREAMK = 5, MDB_GEMM_KNOB_L2_BUDGET_MB = 6 };
+       MDB_GEMM_KNOB_HINT_C = 4, MDB_GEMM_KNOB_STREAMK = 5, MDB_GEMM_KNOB_L2_BUDGET_MB = 6,
+       MDB_GEMM_KNOB_MAX_CLUSTERS = 7 /* cap on co-resident CTA pairs: leaves SMs to a concurrent NCCL kernel */ };
 int mdb_gemm_knob(int knob, int value);
 /* plan of the most recent CTA-pair launch: clusters, raster, group, dp_tiles, sk_clusters, sk_share,
  * hints (100*A + 10*B + C), tiles */

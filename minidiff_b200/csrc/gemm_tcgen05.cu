@@ -511,6 +511,7 @@ extern uint64_t g_gemm_path[MDB_GEMM_NPATHS];
 // tuning knobs (mdb_gemm_knob): -1 = automatic
 int g_knob_raster = -1, g_knob_group = -1, g_knob_hint_a = -1, g_knob_hint_b = -1, g_knob_hint_c = -1;
 int g_knob_streamk = -1;          // -1 auto, 0 never, 1 whenever the split is legal
+int g_knob_max_clusters = -1;     // cap on co-resident CTA pairs (leave SMs to a concurrent NCCL kernel); -1 = all
 int g_knob_l2_budget_mb = 32;     // an operand up to this size is walked whole per band of tiles (stays L2-resident)
 
 constexpr int kPairHi = 4, kPairLo = 3;
@@ -644,6 +645,7 @@ int g_last_plan[8] = {};   // mdb_gemm_last_plan: clusters, raster, group, dp_ti
 static int launch_pair(const CUtensorMap& map_a, const CUtensorMap& map_b, tc::PairParams& q) {
   int max_clusters = 0;
   MDB_TRY(pair_max_clusters(&max_clusters));
+  if (g_knob_max_clusters > 0) max_clusters = std::min(max_clusters, g_knob_max_clusters);
   int clusters = 0;
   bool streamk = false;
   plan_pair(q, max_clusters, &clusters, &streamk);
