@@ -173,6 +173,10 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        for _ in range(20):                      # a very short timed region: wait for a sample taken after it began
+            if any(x[0] >= (self.t0 or 0) for x in self.lines):
+                break
+            time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -330,6 +334,10 @@ def bench_mlp(dev, dist, rank, world, steps, warmup, peaks, use_graph=False):
     from minidiff_b200.parallel import DataParallel
 
     local = GLOBAL_BATCH // world
+    # started first: nvidia-smi takes a few hundred ms to print its first sample on an 8-GPU box, and the
+    # timed region of the 8-GPU run is only ~150 ms long
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", 0)))
+    sampler.start()
     X_np, Y_np = W.mlp_data(local, DIMS[0], DIMS[-1], seed=1000 + 2 * rank)
     params = [md.Tensor(p, allow_grad=True) for p in W.mlp_params(DIMS)]
     X, Y = md.Tensor(X_np), md.Tensor(Y_np)
@@ -341,8 +349,6 @@ def bench_mlp(dev, dist, rank, world, steps, warmup, peaks, use_graph=False):
     def eager_step():
         return W.mlp_train_step(X, Y, params, LR, dp)
 
-    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", 0)))
-    sampler.start()
     loss = None
     for _ in range(warmup):
         loss = eager_step()      # same object lifetimes as the timed loop, so the allocator pool has converged
