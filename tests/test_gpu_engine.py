@@ -739,3 +739,26 @@ def test_capture_refuses_readbacks(md):
         md.capture_graph(bad, warmup=1)
     # the library is usable again afterwards
     np.testing.assert_allclose(md.sum(x * x).item(), 16.0)
+
+
+def test_training_steps_are_bitwise_reproducible(md):
+    """Three C4 training steps at the BASELINE layer dims from the same initial state, run twice: every
+    parameter bit-identical (the GEMM's stream-K fix-up adds partial tiles in cluster order, split
+    reductions fold their partials in a fixed order, nothing uses floating-point atomics)."""
+    X_np, Y_np, ps_np, _, _ = _c4_baseline_case()
+
+    def run():
+        X, Y = md.Tensor(X_np), md.Tensor(Y_np)
+        ps = [md.Tensor(p.copy(), allow_grad=True) for p in ps_np]
+        for _ in range(3):
+            loss = md.mean((mlp(md, X, ps) - Y) ** 2)
+            loss.backward()
+            with md.no_grad():
+                for p in ps:
+                    p -= 0.01 * p.grad
+        return [p.as_numpy() for p in ps], loss.as_numpy()
+
+    (a, la), (b, lb) = run(), run()
+    assert la.tobytes() == lb.tobytes()
+    for x, y in zip(a, b):
+        assert x.tobytes() == y.tobytes()
