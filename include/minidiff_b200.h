@@ -241,6 +241,10 @@ int mdb_isin(const mdb_array* out, const mdb_array* elements, const mdb_array* t
 
 /* counter-based RNG on device (rand / randn / randint / binomial / permutation / choice:
  * backend/numpy.py:131-138, tensor.py:608-659); Philox4x32-10, (seed, offset) select the stream */
+/* offset == MDB_RNG_DEVICE_OFFSET: use (and advance) the library's DEVICE-RESIDENT stream position, so that
+ * a captured CUDA graph draws fresh numbers on every replay; mdb_random_reset sets that position (seed()) */
+#define MDB_RNG_DEVICE_OFFSET UINT64_MAX
+int mdb_random_reset(uint64_t position);
 int mdb_random(const mdb_array* out, int normal, uint64_t seed, uint64_t offset);
 int mdb_random_bits(const mdb_array* out, uint64_t seed, uint64_t offset);            /* raw 32-bit words */
 int mdb_randint(const mdb_array* out, int64_t low, int64_t high, uint64_t seed, uint64_t offset);

@@ -103,6 +103,7 @@ _SIGS = {
     "mdb_gather_rows": (C.c_int, [_A, _A, _A]),
     "mdb_scatter_rows": (C.c_int, [_A, _A, _A, C.c_int]),
     "mdb_random": (C.c_int, [_A, C.c_int, C.c_uint64, C.c_uint64]),
+    "mdb_random_reset": (C.c_int, [C.c_uint64]),
     "mdb_random_bits": (C.c_int, [_A, C.c_uint64, C.c_uint64]),
     "mdb_randint": (C.c_int, [_A, C.c_int64, C.c_int64, C.c_uint64, C.c_uint64]),
     "mdb_binomial": (C.c_int, [_A, C.c_int64, _A, C.c_uint64, C.c_uint64]),

@@ -1302,17 +1302,21 @@ def load(file, **kw):
 
 # ---- random: counter-based Philox on the device; the stream cannot match NumPy's MT19937
 # (SURVEY 8f rank 3), only the distributions do.
-_rng_state = {"seed": 0x5EED5EED, "offset": 0}
+# The stream POSITION lives in device memory (C ABI: offset == MDB_RNG_DEVICE_OFFSET) and is advanced by
+# a one-thread kernel behind every draw, so a captured CUDA graph draws fresh numbers on each replay.
+_rng_state = {"seed": 0x5EED5EED}
+_DEVICE_OFFSET = 2**64 - 1
 
 
 def seed(s: int):
-    _rng_state["seed"], _rng_state["offset"] = int(s) & (2**64 - 1), 0
+    _rng_state["seed"] = int(s) & (2**64 - 1)
+    _lib.ensure_device()
+    check(lib.mdb_random_reset(0))
 
 
 def _random(shape, normal, dtype=F64):
     out = DeviceArray.empty(shape, dtype)
-    check(lib.mdb_random(_byref(out.d), 1 if normal else 0, _rng_state["seed"], _rng_state["offset"]))
-    _rng_state["offset"] += (out.size + 1) // 2
+    check(lib.mdb_random(_byref(out.d), 1 if normal else 0, _rng_state["seed"], _DEVICE_OFFSET))
     return out
 
 
@@ -1331,8 +1335,7 @@ def randint(low, high=None, size=None, dtype=int):
     out = DeviceArray.empty(shape, np.dtype(dtype))
     if out.dtype.kind not in "iu":
         raise TypeError(f"Unsupported dtype {out.dtype!r} for randint")
-    check(lib.mdb_randint(_byref(out.d), int(low), int(high), _rng_state["seed"], _rng_state["offset"]))
-    _rng_state["offset"] += (out.size + 1) // 2
+    check(lib.mdb_randint(_byref(out.d), int(low), int(high), _rng_state["seed"], _DEVICE_OFFSET))
     return out
 
 
@@ -1354,16 +1357,14 @@ def binomial(n, p, size=None):
             raise ValueError("p < 0, p > 1 or p is NaN")
         _fill_imm(pd, float(p))
     out = DeviceArray.empty(shape, I64)
-    check(lib.mdb_binomial(_byref(out.d), n, _byref(pd), _rng_state["seed"], _rng_state["offset"]))
-    _rng_state["offset"] += max(out.size, 1) * ((n + 3) // 4)
+    check(lib.mdb_binomial(_byref(out.d), n, _byref(pd), _rng_state["seed"], _DEVICE_OFFSET))
     return out
 
 
 def _random_permutation_indices(n: int) -> DeviceArray:
     """uniformly random permutation of 0..n-1 on the device: bitonic sort of (random word, i) keys"""
     bits = DeviceArray.empty((max(n, 1),), np.dtype(np.uint32))
-    check(lib.mdb_random_bits(_byref(bits.d), _rng_state["seed"], _rng_state["offset"]))
-    _rng_state["offset"] += (n + 3) // 4
+    check(lib.mdb_random_bits(_byref(bits.d), _rng_state["seed"], _DEVICE_OFFSET))
     out = DeviceArray.empty((n,), I64)
     check(lib.mdb_permutation(_byref(out.d), _byref(bits.d)))
     return out

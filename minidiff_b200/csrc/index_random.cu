@@ -114,8 +114,15 @@ __device__ __forceinline__ void philox4x32(uint64_t ctr, uint64_t seed, uint32_t
   for (int i = 0; i < 4; ++i) out[i] = c[i];
 }
 
+// Stream position: `offset`, or -- when ctr != nullptr -- the library's DEVICE-RESIDENT counter, read by
+// every thread at kernel start and advanced by a one-thread kernel queued right behind (rng_advance).
+// With the position on the device a captured CUDA graph draws fresh numbers on every replay (a host-
+// side offset would be baked into the graph: ADVICE r1).
+__global__ void rng_advance_kernel(unsigned long long* ctr, unsigned long long inc) { *ctr += inc; }
+
 __global__ void __launch_bounds__(256) random_kernel(void* out, int dtype, int64_t n, int normal,
-                                                     uint64_t seed, uint64_t offset) {
+                                                     uint64_t seed, uint64_t offset, const unsigned long long* ctr) {
+  if (ctr) offset = *ctr;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   // each iteration produces 2 values from one Philox block (64 random bits per value)
   for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b * 2 < n; b += stride) {
@@ -137,7 +144,9 @@ __global__ void __launch_bounds__(256) random_kernel(void* out, int dtype, int64
 }
 
 // raw 32-bit words (keys of the permutation sort)
-__global__ void __launch_bounds__(256) random_bits_kernel(uint32_t* out, int64_t n, uint64_t seed, uint64_t offset) {
+__global__ void __launch_bounds__(256) random_bits_kernel(uint32_t* out, int64_t n, uint64_t seed, uint64_t offset,
+                                                          const unsigned long long* ctr) {
+  if (ctr) offset = *ctr;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b * 4 < n; b += stride) {
     uint32_t r[4];
@@ -149,7 +158,9 @@ __global__ void __launch_bounds__(256) random_bits_kernel(uint32_t* out, int64_t
 
 // integers uniform on [low, low + span): 64 random bits scaled by multiply-high (bias < span / 2^64)
 __global__ void __launch_bounds__(256) randint_kernel(void* out, int dtype, int64_t n, long long low,
-                                                      unsigned long long span, uint64_t seed, uint64_t offset) {
+                                                      unsigned long long span, uint64_t seed, uint64_t offset,
+                                                      const unsigned long long* ctr) {
+  if (ctr) offset = *ctr;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b * 2 < n; b += stride) {
     uint32_t r[4];
@@ -165,7 +176,9 @@ __global__ void __launch_bounds__(256) randint_kernel(void* out, int dtype, int6
 
 // binomial(trials, p): sum of `trials` Bernoulli draws per output (p scalar or one value per output)
 __global__ void __launch_bounds__(256) binomial_kernel(long long* out, int64_t n, long long trials, const void* p_arr,
-                                                       int p_dtype, double p_imm, uint64_t seed, uint64_t offset) {
+                                                       int p_dtype, double p_imm, uint64_t seed, uint64_t offset,
+                                                       const unsigned long long* ctr) {
+  if (ctr) offset = *ctr;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const uint64_t blocks_per = (uint64_t)((trials + 3) / 4);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -196,6 +209,34 @@ int mdb_scatter_rows(const mdb_array* dst, const mdb_array* src, const mdb_array
   return rows_op(dst, src, idx, add ? 2 : 1);
 }
 
+// offset == MDB_RNG_DEVICE_OFFSET selects the device-resident stream position
+static unsigned long long* g_rng_ctr = nullptr;
+static int rng_counter(uint64_t offset, unsigned long long** ctr) {
+  *ctr = nullptr;
+  if (offset != MDB_RNG_DEVICE_OFFSET) return 0;
+  if (!g_rng_ctr) {
+    MDB_CUDA(cudaMalloc(&g_rng_ctr, sizeof(unsigned long long)));
+    MDB_CUDA(cudaMemsetAsync(g_rng_ctr, 0, sizeof(unsigned long long), g_stream));
+  }
+  *ctr = g_rng_ctr;
+  return 0;
+}
+static int rng_advance(unsigned long long* ctr, uint64_t blocks) {
+  if (!ctr) return 0;
+  rng_advance_kernel<<<1, 1, 0, g_stream>>>(ctr, (unsigned long long)blocks);
+  MDB_CHECK_LAUNCH();
+  return 0;
+}
+
+int mdb_random_reset(uint64_t position) {
+  MDB_TRY(ensure_init());
+  unsigned long long* ctr = nullptr;
+  MDB_TRY(rng_counter(MDB_RNG_DEVICE_OFFSET, &ctr));
+  MDB_CUDA(cudaMemcpyAsync(ctr, &position, sizeof(position), cudaMemcpyHostToDevice, g_stream));
+  MDB_CUDA(cudaStreamSynchronize(g_stream));      // `position` lives on this stack frame
+  return 0;
+}
+
 static int contiguous_out(const mdb_array* out, const char* who) {
   int64_t st = 1;
   for (int d = out->ndim - 1; d >= 0; --d) {
@@ -211,9 +252,11 @@ int mdb_random_bits(const mdb_array* out, uint64_t seed, uint64_t offset) {
   MDB_TRY(contiguous_out(out, "random_bits"));
   const int64_t n = numel(out);
   if (n == 0) return 0;
-  random_bits_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, g_stream>>>((uint32_t*)out->ptr, n, seed, offset);
+  unsigned long long* ctr = nullptr;
+  MDB_TRY(rng_counter(offset, &ctr));
+  random_bits_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, g_stream>>>((uint32_t*)out->ptr, n, seed, offset, ctr);
   MDB_CHECK_LAUNCH();
-  return 0;
+  return rng_advance(ctr, (uint64_t)(n + 3) / 4);
 }
 
 int mdb_randint(const mdb_array* out, int64_t low, int64_t high, uint64_t seed, uint64_t offset) {
@@ -226,10 +269,12 @@ int mdb_randint(const mdb_array* out, int64_t low, int64_t high, uint64_t seed, 
   MDB_TRY(contiguous_out(out, "randint"));
   const int64_t n = numel(out);
   if (n == 0) return 0;
+  unsigned long long* ctr = nullptr;
+  MDB_TRY(rng_counter(offset, &ctr));
   randint_kernel<<<grid_for((n + 1) / 2, 256), 256, 0, g_stream>>>(out->ptr, out->dtype, n, low,
-                                                                  (unsigned long long)(high - low), seed, offset);
+                                                                  (unsigned long long)(high - low), seed, offset, ctr);
   MDB_CHECK_LAUNCH();
-  return 0;
+  return rng_advance(ctr, (uint64_t)(n + 1) / 2);
 }
 
 int mdb_binomial(const mdb_array* out, int64_t trials, const mdb_array* p, uint64_t seed, uint64_t offset) {
@@ -245,10 +290,12 @@ int mdb_binomial(const mdb_array* out, int64_t trials, const mdb_array* p, uint6
     MDB_REQUIRE(p->imm >= 0.0 && p->imm <= 1.0, "p < 0, p > 1 or p is NaN");
   }
   if (n == 0) return 0;
+  unsigned long long* ctr = nullptr;
+  MDB_TRY(rng_counter(offset, &ctr));
   binomial_kernel<<<grid_for(n, 256), 256, 0, g_stream>>>((long long*)out->ptr, n, trials, p->ptr, p->dtype, p->imm,
-                                                         seed, offset);
+                                                         seed, offset, ctr);
   MDB_CHECK_LAUNCH();
-  return 0;
+  return rng_advance(ctr, (uint64_t)n * (uint64_t)((trials + 3) / 4));
 }
 
 int mdb_random(const mdb_array* out, int normal, uint64_t seed, uint64_t offset) {
@@ -261,10 +308,12 @@ int mdb_random(const mdb_array* out, int normal, uint64_t seed, uint64_t offset)
     st *= out->shape[d];
   }
   if (n == 0) return 0;
+  unsigned long long* ctr = nullptr;
+  MDB_TRY(rng_counter(offset, &ctr));
   random_kernel<<<grid_for((n + 1) / 2, 256), 256, 0, g_stream>>>(out->ptr, out->dtype, n, normal,
-                                                                 seed, offset);
+                                                                 seed, offset, ctr);
   MDB_CHECK_LAUNCH();
-  return 0;
+  return rng_advance(ctr, (uint64_t)(n + 1) / 2);
 }
 
 }  // extern "C"

@@ -53,6 +53,7 @@ LAUNCH(mdb_reduce, int r, const void* o, const void* i, uint32_t m)
 LAUNCH(mdb_elementwise_reduce, int op, const void* o, int n, const void* i, int a)
 LAUNCH(mdb_gemm, const void* c, const void* a, const void* b, int acc)
 LAUNCH(mdb_gemm_batched, const void* c, const void* a, const void* b)
+int mdb_random_reset(uint64_t p) { (void)p; return 0; }
 LAUNCH(mdb_random_bits, const void* o, uint64_t s, uint64_t off)
 LAUNCH(mdb_randint, const void* o, int64_t lo, int64_t hi, uint64_t s, uint64_t off)
 LAUNCH(mdb_binomial, const void* o, int64_t n, const void* p, uint64_t s, uint64_t off)

@@ -321,3 +321,32 @@ def test_arange_and_stacking_stay_on_the_device(B):
     s = B.asarray(rows)
     assert s.shape == (4, 3) and launches() - l0 == 4          # one copy per row, nothing staged through the host
     np.testing.assert_array_equal(s.numpy(), np.stack([r.numpy() for r in rows]))
+
+
+def test_rng_position_lives_on_the_device(B):
+    """seed() makes the stream reproducible; a captured CUDA graph draws FRESH numbers on every replay
+    (the stream position is device-resident and advanced by a kernel inside the graph)."""
+    import minidiff_b200 as md
+
+    B.seed(123)
+    a1, b1 = B.rand(1000).numpy(), B.randn(7, 9).numpy()
+    B.seed(123)
+    a2, b2 = B.rand(1000).numpy(), B.randn(7, 9).numpy()
+    np.testing.assert_array_equal(a1, a2)
+    np.testing.assert_array_equal(b1, b2)
+    assert not np.array_equal(a1, B.rand(1000).numpy())
+    buf = md.Tensor(B.zeros((4096,), dtype=np.float64))
+
+    def step():
+        with md.no_grad():
+            buf[...] = md.Tensor(B.rand(4096))
+        return buf
+
+    g = md.capture_graph(step)
+    draws = []
+    for _ in range(3):
+        g.replay()
+        draws.append(buf.as_numpy().copy())
+    g.close()
+    assert not np.array_equal(draws[0], draws[1]) and not np.array_equal(draws[1], draws[2])
+    assert all(0.45 < d.mean() < 0.55 for d in draws)
