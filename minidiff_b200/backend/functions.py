@@ -806,7 +806,7 @@ def matmul(x, y, **_kw):
     yv = y.view(y.shape + (1,), y.estrides + (0,)) if y.ndim == 1 else y
     if dt == F32 and xv.ndim == 2 and yv.ndim == 2:
         r = _gemm(xv, yv)                 # tcgen05 3xTF32 (CUDA-core kernel for small / odd shapes)
-    elif dt == F32 and xv.shape[-2] * yv.shape[-1] * xv.shape[-1] >= (1 << 24) and len(
+    elif dt == F32 and xv.shape[-2] * yv.shape[-1] * xv.shape[-1] >= (1 << 27) and len(
             broadcast_shapes([xv.shape[:-2], yv.shape[:-2]])) <= 2 and math.prod(
             broadcast_shapes([xv.shape[:-2], yv.shape[:-2]])) <= 64:
         # a few LARGE stacked matrices: one tensor-core GEMM each beats the batched CUDA-core kernel

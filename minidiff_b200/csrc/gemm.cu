@@ -141,6 +141,85 @@ __global__ void __launch_bounds__(256) gemm_simt_batched(const BatchParams p, co
   }
 }
 
+// fp32 variant for matrices of at least 128 x 128: 128 x 128 x 8 tiles, 8 x 8 outputs per thread read from
+// shared memory as float4, the next k-tile prefetched into registers while the current one is used.
+// (The 64 x 64 kernel above measured 1.5 TFLOP/s on 64 stacked 256^3 products: 4 x 4 outputs per thread
+// leave it bound by shared-memory loads.)
+__global__ void __launch_bounds__(256) gemm_simt_batched_f32_128(const BatchParams p, const float* __restrict__ A,
+                                                                 const float* __restrict__ B, float* C) {
+  constexpr int BM = 128, BN = 128, BK = 8;
+  __shared__ __align__(16) float As[2][BK][BM];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int tr = (tid / 16) * 8, tc = (tid % 16) * 8;
+  const bool a_k_fast = (p.sak == 1), b_n_fast = (p.sbn == 1);
+  // loader mapping: 1024 elements per operand tile, 4 per thread, walking the operand's unit-stride axis
+  int am[4], ak[4], bn[4], bk[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int e = tid + i * 256;
+    am[i] = a_k_fast ? e / BK : e % BM; ak[i] = a_k_fast ? e % BK : e / BM;
+    bn[i] = b_n_fast ? e % BN : e / BK; bk[i] = b_n_fast ? e / BN : e % BK;
+  }
+  for (int64_t batch = blockIdx.z; batch < p.batches; batch += gridDim.z) {
+    int64_t rem = batch, oa = 0, ob = 0, oc = 0;
+    for (int d = p.nbatch_dims - 1; d >= 0; --d) {
+      const int64_t q = rem / p.bshape[d], i = rem - q * p.bshape[d];
+      rem = q;
+      oa += i * p.sa[d]; ob += i * p.sb[d]; oc += i * p.sc[d];
+    }
+    const float* Ab = A + oa;
+    const float* Bb = B + ob;
+    float* Cb = C + oc;
+    float acc[8][8] = {};
+    float ra[4], rb[4];
+    auto fetch = [&](int k0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int gm = m0 + am[i], gk = k0 + ak[i];
+        ra[i] = (gm < p.M && gk < p.K) ? Ab[(int64_t)gm * p.sam + (int64_t)gk * p.sak] : 0.f;
+        const int gn = n0 + bn[i], gkb = k0 + bk[i];
+        rb[i] = (gn < p.N && gkb < p.K) ? Bb[(int64_t)gkb * p.sbk + (int64_t)gn * p.sbn] : 0.f;
+      }
+    };
+    auto stash = [&](int buf) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { As[buf][ak[i]][am[i]] = ra[i]; Bs[buf][bk[i]][bn[i]] = rb[i]; }
+    };
+    fetch(0);
+    stash(0);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = 0; k0 < p.K; k0 += BK) {
+      const bool more = k0 + BK < p.K;
+      if (more) fetch(k0 + BK);
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) {
+        const float4 a0 = *(const float4*)&As[buf][kk][tr], a1 = *(const float4*)&As[buf][kk][tr + 4];
+        const float4 b0 = *(const float4*)&Bs[buf][kk][tc], b1 = *(const float4*)&Bs[buf][kk][tc + 4];
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      if (more) stash(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int gm = m0 + tr + i, gn = n0 + tc + j;
+        if (gm < p.M && gn < p.N) Cb[(int64_t)gm * p.scm + (int64_t)gn * p.scn] = acc[i][j];
+      }
+    __syncthreads();
+  }
+}
+
 static int gemm_simt(const mdb_array* c, const mdb_array* a, const mdb_array* b, int accumulate) {
   const int M = (int)a->shape[0], K = (int)a->shape[1], N = (int)b->shape[1];
   dim3 grid((N + 63) / 64, (M + 63) / 64);
@@ -272,7 +351,10 @@ int mdb_gemm_batched(const mdb_array* c, const mdb_array* a, const mdb_array* b)
   if (p.batches == 0 || p.M == 0 || p.N == 0) return 0;
   ProfScope prof(PROF_GEMM, 2.0 * (double)p.batches * p.M * (double)p.K * p.N);
   dim3 grid((p.N + 63) / 64, (p.M + 63) / 64, (unsigned)std::min<int64_t>(p.batches, 32768));
-  if (a->dtype == MDB_F32)
+  if (a->dtype == MDB_F32 && p.M >= 128 && p.N >= 128) {
+    dim3 grid128((p.N + 127) / 128, (p.M + 127) / 128, (unsigned)std::min<int64_t>(p.batches, 32768));
+    gemm_simt_batched_f32_128<<<grid128, 256, 0, g_stream>>>(p, (const float*)a->ptr, (const float*)b->ptr, (float*)c->ptr);
+  } else if (a->dtype == MDB_F32)
     gemm_simt_batched<float><<<grid, 256, 0, g_stream>>>(p, (const float*)a->ptr, (const float*)b->ptr, (float*)c->ptr);
   else
     gemm_simt_batched<double><<<grid, 256, 0, g_stream>>>(p, (const double*)a->ptr, (const double*)b->ptr, (double*)c->ptr);

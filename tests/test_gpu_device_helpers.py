@@ -262,7 +262,8 @@ def test_float64_matmul_needs_no_cubic_temporary(B):
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("sa,sb", [((6, 40, 30), (6, 30, 20)), ((2, 3, 17, 9), (3, 9, 5)), ((5, 1, 8, 12), (1, 4, 12, 7)),
-                                   ((8, 33), (4, 33, 6)), ((3, 2, 10, 4), (4,)), ((7,), (2, 7, 5))])
+                                   ((8, 33), (4, 33, 6)), ((3, 2, 10, 4), (4,)), ((7,), (2, 7, 5)),
+                                   ((4, 130, 33), (4, 33, 257)), ((2, 1, 300, 129), (3, 129, 200))])
 def test_stacked_matmul_is_one_launch_and_broadcasts(B, dtype, sa, sb):
     rng = np.random.default_rng(len(sa) + len(sb))
     a, b = rng.standard_normal(sa).astype(dtype), rng.standard_normal(sb).astype(dtype)
