@@ -400,6 +400,71 @@ int mdb_unravel_index(const mdb_array* out, const mdb_array* indices, int ndim, 
   return 0;
 }
 
+}  // extern "C"
+
+namespace mdb {
+// ascending in-place sort of `padded` (a power of two >= kSortTile) 64-bit keys
+static int bitonic_sort_u64(unsigned long long* k, int64_t padded) {
+  const unsigned tiles = (unsigned)(padded / kSortTile);
+  bitonic_local_kernel<<<tiles, 1024, 0, g_stream>>>(k, padded, 2, kSortTile);
+  MDB_CHECK_LAUNCH();
+  for (int64_t kk = 2 * kSortTile; kk <= padded; kk <<= 1) {
+    for (int64_t j = kk >> 1; j >= kSortTile; j >>= 1) {
+      bitonic_global_kernel<<<(unsigned)((padded / 2 + 255) / 256), 256, 0, g_stream>>>(k, padded, j, kk);
+      MDB_CHECK_LAUNCH();
+    }
+    bitonic_local_kernel<<<tiles, 1024, 0, g_stream>>>(k, padded, kk, kk);
+    MDB_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+// isin for LARGE test sets: order-preserving 64-bit keys of the test elements, sorted once, then one
+// binary search per element (the all-pairs kernel is O(n*m))
+template <typename T> __device__ __forceinline__ unsigned long long order_key(T v);
+template <> __device__ __forceinline__ unsigned long long order_key<long long>(long long v) {
+  return (unsigned long long)v ^ 0x8000000000000000ull;
+}
+template <> __device__ __forceinline__ unsigned long long order_key<double>(double v) {
+  if (v == 0.0) v = 0.0;                                   // -0.0 == +0.0
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+template <typename T>
+__global__ void __launch_bounds__(256) isin_keys_kernel(const void* test, int dtype, int64_t m, int64_t padded,
+                                                        unsigned long long* keys) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= padded) return;
+  if (i < m) {
+    const T v = load_as<T>(test, dtype, i);
+    keys[i] = (v != v) ? ~0ull : order_key<T>(v);        // NaN never equals anything: park it with the padding
+  } else {
+    keys[i] = ~0ull;
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) isin_search_kernel(const void* elem, int dtype, int64_t n,
+                                                          const unsigned long long* keys, int64_t m,
+                                                          unsigned char* out, int invert) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const T v = load_as<T>(elem, dtype, i);
+  bool found = false;
+  if (v == v) {
+    const unsigned long long key = order_key<T>(v);
+    int64_t lo = 0, hi = m;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (keys[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    found = lo < m && keys[lo] == key && key != ~0ull;
+  }
+  out[i] = (unsigned char)(found != (invert != 0));
+}
+}  // namespace mdb
+
+extern "C" {
+
 int mdb_isin(const mdb_array* out, const mdb_array* elements, const mdb_array* test, int invert) {
   MDB_TRY(ensure_init());
   MDB_REQUIRE(out && elements && test && out->ptr && elements->ptr, "isin: device arrays required");
@@ -410,7 +475,27 @@ int mdb_isin(const mdb_array* out, const mdb_array* elements, const mdb_array* t
   if (n == 0) return 0;
   MDB_REQUIRE(m == 0 || test->ptr, "isin: test elements missing");
   const unsigned grid = (unsigned)((n + 255) / 256);
-  if (is_int_dtype(elements->dtype) && is_int_dtype(test->dtype))
+  const bool ints = is_int_dtype(elements->dtype) && is_int_dtype(test->dtype);
+  if (m > 4096) {
+    // large test set: sort its order-preserving keys once, binary-search every element
+    int64_t padded = kSortTile;
+    while (padded < m) padded <<= 1;
+    TempBuf keys;
+    MDB_TRY(keys.alloc((size_t)padded * sizeof(unsigned long long)));
+    unsigned long long* k = (unsigned long long*)keys.ptr;
+    const unsigned kgrid = (unsigned)((padded + 255) / 256);
+    if (ints) isin_keys_kernel<long long><<<kgrid, 256, 0, g_stream>>>(test->ptr, test->dtype, m, padded, k);
+    else isin_keys_kernel<double><<<kgrid, 256, 0, g_stream>>>(test->ptr, test->dtype, m, padded, k);
+    MDB_CHECK_LAUNCH();
+    MDB_TRY(bitonic_sort_u64(k, padded));
+    if (ints) isin_search_kernel<long long><<<grid, 256, 0, g_stream>>>(elements->ptr, elements->dtype, n, k, m,
+                                                                     (unsigned char*)out->ptr, invert);
+    else isin_search_kernel<double><<<grid, 256, 0, g_stream>>>(elements->ptr, elements->dtype, n, k, m,
+                                                               (unsigned char*)out->ptr, invert);
+    MDB_CHECK_LAUNCH();
+    return 0;
+  }
+  if (ints)
     isin_kernel<long long><<<grid, 256, 0, g_stream>>>(elements->ptr, elements->dtype, n, test->ptr, test->dtype, m,
                                                       (unsigned char*)out->ptr, invert);
   else
@@ -437,17 +522,7 @@ int mdb_permutation(const mdb_array* out, const mdb_array* bits) {
   unsigned long long* k = (unsigned long long*)keys.ptr;
   perm_keys_kernel<<<(unsigned)((padded + 255) / 256), 256, 0, g_stream>>>(k, (const float*)bits->ptr, n, padded);
   MDB_CHECK_LAUNCH();
-  const unsigned tiles = (unsigned)(padded / kSortTile);
-  bitonic_local_kernel<<<tiles, 1024, 0, g_stream>>>(k, padded, 2, kSortTile);
-  MDB_CHECK_LAUNCH();
-  for (int64_t kk = 2 * kSortTile; kk <= padded; kk <<= 1) {
-    for (int64_t j = kk >> 1; j >= kSortTile; j >>= 1) {
-      bitonic_global_kernel<<<(unsigned)((padded / 2 + 255) / 256), 256, 0, g_stream>>>(k, padded, j, kk);
-      MDB_CHECK_LAUNCH();
-    }
-    bitonic_local_kernel<<<tiles, 1024, 0, g_stream>>>(k, padded, kk, kk);
-    MDB_CHECK_LAUNCH();
-  }
+  MDB_TRY(bitonic_sort_u64(k, padded));
   perm_extract_kernel<<<(unsigned)((n + 255) / 256), 256, 0, g_stream>>>(k, (long long*)out->ptr, n);
   MDB_CHECK_LAUNCH();
   return 0;

@@ -351,3 +351,19 @@ def test_rng_position_lives_on_the_device(B):
     g.close()
     assert not np.array_equal(draws[0], draws[1]) and not np.array_equal(draws[1], draws[2])
     assert all(0.45 < d.mean() < 0.55 for d in draws)
+
+
+def test_isin_large_test_set_uses_the_sorted_path(B):
+    rng = np.random.default_rng(4)
+    e = rng.integers(-10**6, 10**6, 300000)
+    t = rng.integers(-10**6, 10**6, 50000)                   # > 4096 test elements: sort + binary search
+    np.testing.assert_array_equal(B.isin(B.asarray(e), B.asarray(t)).numpy(), np.isin(e, t))
+    np.testing.assert_array_equal(B.isin(B.asarray(e), B.asarray(t), invert=True).numpy(), np.isin(e, t, invert=True))
+    ef = np.round(rng.standard_normal(200000), 2)
+    tf = np.round(rng.standard_normal(9000), 2)
+    tf[:3] = [np.nan, -0.0, np.inf]
+    ef[:4] = [np.nan, 0.0, np.inf, -np.inf]
+    np.testing.assert_array_equal(B.isin(B.asarray(ef), B.asarray(tf)).numpy(), np.isin(ef, tf))
+    big = np.array([2**62 + 1, 2**62, -2**62 - 1, 5])
+    tb = np.concatenate([np.arange(5000), [2**62 + 1, -2**62 - 1]])
+    np.testing.assert_array_equal(B.isin(B.asarray(big), B.asarray(tb)).numpy(), [True, False, True, True])
