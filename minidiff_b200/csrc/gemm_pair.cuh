@@ -199,7 +199,7 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   } else if (warp == 0) {
     // ===================================== TMA producer (both CTAs) ==========================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (lane == 0) {
+    if (elect_one()) {
       const uint64_t pol_a = l2_policy(p.hint_a), pol_b = l2_policy(p.hint_b);
       Ring hi;
       long long w_empty = 0, t_all = MDB_T0();
@@ -264,7 +264,7 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
           mbar_wait_cluster(&lo_full[lo.slot], lo.phase);    // raw + lo tiles ready in both CTAs
           MDB_TACC(w_lo, tw2);
           tcgen05_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {
             const uint32_t a_hi = smem_u32(smem + hi.slot * S::SLOT_BYTES), b_hi = a_hi + S::A_BYTES;
             const uint32_t a_lo = smem_u32(lo_ring + lo.slot * S::SLOT_BYTES), b_lo = a_lo + S::A_BYTES;
 #pragma unroll

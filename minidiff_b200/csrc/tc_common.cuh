@@ -53,6 +53,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// One lane of a fully active warp, chosen by elect.sync.  ptxas recognises the pattern and compiles the
+// region it guards on the UNIFORM datapath: descriptors / addresses live in uniform registers and
+// UTCHMMA / UTMALDG take them directly.  With `if (lane == 0)` the same code is a divergent region and
+// every tcgen05.mma is preceded by an ELECT + 5 x R2UR.BROADCAST "waterfall" loop (11 instructions with
+// long latencies per MMA): measured here, the single issuing thread then needed ~2140 cycles per k-block
+// for 12 MMAs that take 1536 tensor-core cycles -- the kernel was ISSUE-bound.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
