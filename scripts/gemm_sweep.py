@@ -72,8 +72,7 @@ variants = [("old_r0g8", dict(raster=0, group=8, hint_a=0, hint_b=0, hint_c=0, s
             ("r0g16", dict(raster=0, group=16, streamk=0))]
 if os.environ.get("SWEEP") == "flags":
     # kernel-flag A/B (mdb_gemm_tune bits) instead of planner knobs
-    variants = [("base", dict(_flags=4 | 32)), ("base1", dict(_flags=4 | 32)), ("base2", dict(_flags=4 | 32)),
-                ("base3", dict(_flags=4 | 32))]
+    variants = [("base", dict(_flags=4 | 32)), ("lo_rounded", dict(_flags=32)), ("base2", dict(_flags=4 | 32))]
 check(lib.mdb_gemm_tune(4 | 32))
 for name, (M, K, N), ta, tb in shapes:
     if only and name not in only:
