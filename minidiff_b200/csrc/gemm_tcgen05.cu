@@ -157,7 +157,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   } else if (warp == 0) {
     // ===================================== TMA producer =====================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (lane == 0) {
+    if (elect_one()) {                 // uniform-datapath issue, see tc_common.cuh
       Ring hi, lo;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         int m_blk, n_blk;
@@ -236,7 +236,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         const uint32_t a_hi = smem_u32(smem + hi.slot * S::SLOT_BYTES), b_hi = a_hi + S::A_BYTES;
         const uint32_t a_lo = smem_u32(lo_ring + lo.slot * S::SLOT_BYTES), b_lo = a_lo + S::A_BYTES;
         const bool early = p.flags & 1;
-        if (early && lane == 0) {                        // hi*hi needs only the raw tiles: issue it
+        if (early && elect_one()) {                      // hi*hi needs only the raw tiles: issue it
 #pragma unroll                                           // while the converters still work on lo
           for (int k = 0; k < BK / UMMA_K; ++k)
             umma_tf32(tmem_d, make_desc(a_hi + k * a_kstep, a_lbo, a_sbo, a_lt),
@@ -245,7 +245,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         __syncwarp();
         mbar_wait(&lo_full[lo.slot], lo.phase);          // lo tiles written (converters / TMA)
         tcgen05_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t da_hi = make_desc(a_hi + k * a_kstep, a_lbo, a_sbo, a_lt);
