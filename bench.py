@@ -45,7 +45,7 @@ sys.path.insert(0, ROOT)
 
 # ncu --set full capture of one C4 step at N=1 (profiles/r02_ncu_mlp_step_gemm.md): DRAM bytes per GEMM
 # launch, and the algorithmic figure beside it (each operand read once + C written once, 8 GEMMs/step)
-GEMM_TRAFFIC_BYTES_PER_LAUNCH = 3.676e9
+GEMM_TRAFFIC_BYTES_PER_LAUNCH = 2.851e9
 GEMM_ALGORITHMIC_BYTES_PER_LAUNCH = (
     # fwd1, fwd2, fwd3 (X@W), dW3, dh2, dW2, dh1, dW1 at B=65536, D=(1024,4096,4096,1024)
     sum(4.0 * (m * k + k * n + m * n) for m, k, n in [
@@ -59,7 +59,7 @@ C2_TRAFFIC_SRC = ("dram__bytes_read.sum + dram__bytes_write.sum over the 13 laun
                   "in the 126 MB L2 when the next op reads it)")
 GEMM_TRAFFIC_SRC = ("dram__bytes_read.sum + dram__bytes_write.sum averaged over the 8 GEMM launches of one C4 step "
                     "(ncu --set full, profiles/r02_ncu_mlp_step_gemm.md)")
-C3_TRAFFIC_BYTES_PER_LAUNCH = 3.129e9
+C3_TRAFFIC_BYTES_PER_LAUNCH = 2.571e9
 C3_TRAFFIC_SRC = ("dram__bytes_read.sum + dram__bytes_write.sum per 8192^3 launch of the shipped pair kernel "
                   "(ncu --set full, profiles/r02_ncu_c3_gemm.md)")
 GLOBAL_BATCH = int(os.environ.get("MDB_BENCH_GLOBAL_BATCH", 65536))   # override for experiments only (scripts/dp_contention.sh)
