@@ -749,10 +749,13 @@ def bench_c5(dev, steps, warmup, peaks, batch=8192):
             "roofline": tensor_roofline(tf, peaks, traffic=None, gemm_share_of_iter=(g_ms / steps) / ms)}
 
 
-def bench_c4_fused(dev, steps, warmup, peaks):
-    """The C4 training step written with the stateful fused ops: md.linear_relu(X, W, b)
+def bench_c4_fused(dev, steps, warmup, peaks, fused=True, split="3xtf32"):
+    """fused=True: the C4 training step written with the stateful fused ops: md.linear_relu(X, W, b)
     = one tcgen05 GEMM with bias + ReLU in its epilogue, md.linear for the output layer; backward
-    masks the upstream gradient once per layer (or inside the dX GEMM epilogue of the layer above)."""
+    masks the upstream gradient once per layer (or inside the dX GEMM epilogue of the layer above).
+    fused=False: the headline step (workloads.mlp_train_step).  split: operand split of the tensor-core GEMM
+    (backend.set_matmul_split): "3xtf32" is the default everywhere else in this file; "fast" = one TF32 MMA + two
+    BF16 cross-term MMAs per product, opt-in because its error sits at the edge of the GEMM tolerance."""
     md = dev.md
     from minidiff_b200 import workloads as W
 
@@ -762,6 +765,8 @@ def bench_c4_fused(dev, steps, warmup, peaks):
     del X_np, Y_np
 
     def step():
+        if not fused:
+            return W.mlp_train_step(X, Y, params, LR, None)
         h = md.linear_relu(X, params[0], params[1])
         h = md.linear_relu(h, params[2], params[3])
         loss = md.mean((md.linear(h, params[4], params[5]) - Y) ** 2)
@@ -771,28 +776,41 @@ def bench_c4_fused(dev, steps, warmup, peaks):
                 p -= LR * p.grad
         return loss
 
-    loss = warm_until_stable(dev, step, warmup)
-    e0, e1 = dev.event(), dev.event()
-    dev.prof(True)
-    dev.gemm_paths(reset=True)
-    l0 = dev.launches()
-    dev.record(e0)
-    for _ in range(steps):
-        loss = step()
-    dev.record(e1)
-    dev.sync()
+    md.backend.set_matmul_split(split)
+    try:
+        loss = warm_until_stable(dev, step, warmup)
+        e0, e1 = dev.event(), dev.event()
+        dev.prof(True)
+        dev.gemm_paths(reset=True)
+        l0 = dev.launches()
+        dev.record(e0)
+        for _ in range(steps):
+            loss = step()
+        dev.record(e1)
+        dev.sync()
+    finally:
+        md.backend.set_matmul_split("3xtf32")
     ms = dev.elapsed_ms(e0, e1) / steps
     g_ms, g_n, g_fl = dev.prof_read(2)
     ew_ms, ew_n, ew_b = dev.prof_read(0)
     red_ms, red_n, red_b = dev.prof_read(1)
     dev.prof(False)
     tf = g_fl / (g_ms * 1e-3) / 1e12
-    return {"workload": "C4 training step written with md.linear_relu / md.linear (fused stateful ops)",
+    roof = tensor_roofline(tf, peaks, launches=int(g_n), share_of_step=(g_ms / steps) / ms)
+    name = "C4 training step written with md.linear_relu / md.linear (fused stateful ops)" if fused else \
+        "C4 training step (same code as the headline)"
+    if split == "fast":
+        name += "; GEMM operand split 'fast' (backend.set_matmul_split)"
+        roof["pipe_frac"] = 2.0 * roof["frac"]
+        roof["note"] = ("fast split: one TF32 MMA + two BF16 MMAs (half the tensor-pipe time each) per fp32 product = 2 "
+                        "TF32-equivalents, so pipe_frac = 2*frac; rms error 1.4e-6 of the result's rms instead of 0.5e-6 "
+                        "(tests/test_gpu_gemm.py::test_operand_splits_accuracy_against_float64)")
+    return {"workload": name, "gemm_split": split,
             "ms_per_step": ms, "samples_per_s": GLOBAL_BATCH / (ms * 1e-3),
             "launches_per_step": (dev.launches() - l0) / steps, "loss": float(loss.item()),
             "gemm_paths": dev.gemm_paths(),
             "elementwise_ms_per_step": ew_ms / steps, "reduce_ms_per_step": red_ms / steps,
-            "roofline": tensor_roofline(tf, peaks, launches=int(g_n), share_of_step=(g_ms / steps) / ms)}
+            "roofline": roof}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -1092,6 +1110,10 @@ def main():
                                "c3_matmul": bench_c3(dev, max(2, min(args.steps, 5)), warmup, peaks),
                                "c5_hvp": bench_c5(dev, max(args.steps, 10), warmup, peaks),
                                "c4_fused": bench_c4_fused(dev, max(5, min(args.steps, 10)), warmup, peaks),
+                               "c4_fast_split": bench_c4_fused(dev, max(5, min(args.steps, 10)), warmup, peaks,
+                                                               fused=False, split="fast"),
+                               "c4_fused_fast_split": bench_c4_fused(dev, max(5, min(args.steps, 10)), warmup, peaks,
+                                                                     fused=True, split="fast"),
                                "c4_reference_engine_dropin": bench_c4_reference_engine(dev, 5, warmup)}
         if not args.skip_cpu:
             # the unmodified reference on its NumPy backend, on this box's host cores, same workloads

@@ -192,7 +192,14 @@ int mdb_gemm_stats(uint64_t* counts, int reset);
  * (0 none, 1 evict_first, 2 evict_last), stream-K (0 never, 1 whenever legal) */
 enum { MDB_GEMM_KNOB_RASTER = 0, MDB_GEMM_KNOB_GROUP = 1, MDB_GEMM_KNOB_HINT_A = 2, MDB_GEMM_KNOB_HINT_B = 3,
        MDB_GEMM_KNOB_HINT_C = 4, MDB_GEMM_KNOB_STREAMK = 5, MDB_GEMM_KNOB_L2_BUDGET_MB = 6,
-       MDB_GEMM_KNOB_MAX_CLUSTERS = 7 /* cap on co-resident CTA pairs: leaves SMs to a concurrent NCCL kernel */ };
+       MDB_GEMM_KNOB_MAX_CLUSTERS = 7 /* cap on co-resident CTA pairs: leaves SMs to a concurrent NCCL kernel */,
+       MDB_GEMM_KNOB_SPLIT = 8 /* CTA-pair kernel: 0 and -1 (default) = 3xTF32 (three TF32 MMAs per product); 1 = "fast" split: one TF32 MMA + the two
+                                   cross terms as BF16 MMAs (8 instead of 12 tensor-core instructions per k-block; rms error 1.4e-6 instead
+                                   of 0.5e-6 of the result's rms, maximum ~1e-5: at the edge of the GEMM tolerance, hence opt-in) */,
+       MDB_GEMM_KNOB_CHUNK = 9 /* CTA-pair kernel: k-blocks (32 K each) accumulated in tensor memory before the partial sum is promoted to
+                                   fp32 registers (the tensor core truncates on accumulate); -1 = default */,
+       MDB_GEMM_KNOB_RZ_GAIN = 10 /* CTA-pair kernel: compensation of that truncation's bias per MMA instruction, in units of 1e-10
+                                     (0 = off, -1 = default) */ };
 int mdb_gemm_knob(int knob, int value);
 /* plan of the most recent CTA-pair launch: clusters, raster, group, dp_tiles, sk_clusters, sk_share,
  * hints (100*A + 10*B + C), tiles */

@@ -9,7 +9,7 @@ namespace mdb {
 
 int gemm_tcgen05(const mdb_array* c, const mdb_array* a, const mdb_array* b, int accumulate, const GemmEpilogue* epi);
 extern int g_last_plan[8];
-extern int g_knob_raster, g_knob_group, g_knob_hint_a, g_knob_hint_b, g_knob_hint_c, g_knob_streamk, g_knob_l2_budget_mb, g_knob_max_clusters;
+extern int g_knob_raster, g_knob_group, g_knob_hint_a, g_knob_hint_b, g_knob_hint_c, g_knob_streamk, g_knob_l2_budget_mb, g_knob_max_clusters, g_knob_split, g_knob_chunk, g_knob_rz_gain;
 static int g_force_path = 0;
 extern int g_gemm_flags;
 // launches per GEMM kernel since the last reset (mdb_gemm_stats): tests assert with it that a
@@ -275,6 +275,9 @@ int mdb_gemm_knob(int knob, int value) {
     case MDB_GEMM_KNOB_HINT_C: g_knob_hint_c = value; break;
     case MDB_GEMM_KNOB_STREAMK: g_knob_streamk = value; break;
     case MDB_GEMM_KNOB_MAX_CLUSTERS: g_knob_max_clusters = value; break;
+    case MDB_GEMM_KNOB_SPLIT: g_knob_split = value; break;
+    case MDB_GEMM_KNOB_CHUNK: g_knob_chunk = value; break;
+    case MDB_GEMM_KNOB_RZ_GAIN: g_knob_rz_gain = value; break;
     case MDB_GEMM_KNOB_L2_BUDGET_MB: g_knob_l2_budget_mb = value > 0 ? value : 32; break;
     default: return set_error(MDB_EINVAL, "unknown GEMM knob %d", knob);
   }

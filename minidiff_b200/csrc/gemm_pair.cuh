@@ -70,6 +70,8 @@ struct PairParams {
   int64_t ld_mask;
   int hint_a, hint_b, hint_c;      // L2 eviction hints: 0 none, 1 evict_first, 2 evict_last
   int flags;
+  float rz_gain;                   // per-MMA-instruction compensation of the accumulator's round-toward-zero bias (see epilogue)
+  int chunk;                       // k-blocks per in-TMEM accumulation chain before the promotion to fp32 registers
   unsigned long long* timing;      // MDB_GEMM_TIMING=1: per-CTA stall-cycle counters (16 per CTA), else null
 };
 
@@ -150,7 +152,105 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
   return v;
 }
 
-template <int kHi, int kLo, bool kTiming>
+// ---- TF32 + 2 x BF16 split ("hybrid", kHybrid) ---------------------------------------------------------
+// a*b = a_t*b_t + a_l*b + a*b_l - a_l*b_l, a_t = what the TF32 datapath sees (top 19 bits), a_l = a - a_t
+// (exact, < 2^-10 |a|).  The big term runs as ONE kind::tf32 MMA on the raw fp32 tiles; the two cross
+// terms only need ~8 significant bits per factor to stay below 2^-18 of the product, so they run as
+// kind::f16 MMAs on BF16 tiles (K = 16 per instruction: half the instructions and half the shared-memory
+// bytes of a TF32 cross term).  Per k-block: 4 + 2 + 2 = 8 tensor-core instructions instead of 12.
+// The converters write, per operand, hb = bf16(x) and lb = bf16(x - x_t) as K-MAJOR 128 x 32 BF16 tiles
+// (64-byte rows, SWIZZLE_64B: 16-B chunk ^= (row >> 1) & 3, 8-row / 512-B atoms) whatever the layout of
+// the raw tile -- an MN-major raw tile is transposed in registers on the way.
+__device__ __forceinline__ void lds128(float* v, uint32_t addr) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint32_t* r) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+// (x0, x1) = two consecutive k  ->  bf16x2 of the values and of their TF32 remainders (x0 in the low half)
+__device__ __forceinline__ void split_pack(float x0, float x1, uint32_t& hb, uint32_t& lb) {
+  const float l0 = __fsub_rn(x0, __uint_as_float(__float_as_uint(x0) & 0xFFFFE000u));
+  const float l1 = __fsub_rn(x1, __uint_as_float(__float_as_uint(x1) & 0xFFFFE000u));
+  asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(hb) : "f"(x1), "f"(x0));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lb) : "f"(l1), "f"(l0));
+}
+// K-major raw tile (128 rows x 128 B, SWIZZLE_128B).  Converter warp cw, iteration it: rows (it*4+cw)*8 + (lane&7),
+// k range 8j .. 8j+7 (j = lane >> 3) = logical 16-B chunks 2j, 2j+1.  A quarter-warp reads / writes 8 distinct
+// 16-B bank groups in both directions.
+template <int kHalf>
+__device__ __forceinline__ void cv_load_k(float (&v)[32], uint32_t src, int cw, int lane) {
+  const int r7 = lane & 7, j = lane >> 3;
+  const uint32_t p0 = (uint32_t)((2 * j) ^ r7) << 4;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int it = kHalf * 2 + i;
+    const uint32_t row = src + (uint32_t)(((it * 4 + cw) * 8 + r7) * 128);
+    lds128(&v[it * 8], row + p0);
+    lds128(&v[it * 8 + 4], row + (p0 ^ 16u));
+  }
+}
+template <int kHalf>
+__device__ __forceinline__ void cv_proc_k(const float (&v)[32], uint32_t hb, uint32_t lb, int cw, int lane) {
+  const int r7 = lane & 7, j = lane >> 3;
+  const uint32_t o = (uint32_t)(r7 * 64 + ((j ^ ((lane >> 1) & 3)) << 4));
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int it = kHalf * 2 + i;
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) split_pack(v[it * 8 + 2 * e], v[it * 8 + 2 * e + 1], h[e], l[e]);
+    const uint32_t off = (uint32_t)((it * 4 + cw) * 512) + o;
+    sts128(hb + off, h);
+    sts128(lb + off, l);
+  }
+}
+// MN-major raw tile (4 chunks of [32 k][32 m] fp32, 128-B rows, SWIZZLE_128B_ATOM_32B: 32-B unit ^= k & 3).
+// Thread: chunk cw, 4 rows m = 8u + 4h + {0..3} (one float4 per k), 8 consecutive k (kg = u ^ q, q = lane >> 3, so
+// that the 16-B stores of a quarter-warp fall into distinct bank groups; lanes with h = 1 store their row pairs
+// in swapped order for the same reason).
+template <int kHalf>
+__device__ __forceinline__ void cv_load_mn(float (&v)[32], uint32_t src, int cw, int lane) {
+  const int q = lane >> 3, u = (lane >> 1) & 3, h = lane & 1, kg = u ^ q;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int s = kHalf * 4 + i;
+    lds128(&v[s * 4], src + (uint32_t)(cw * 4096 + (kg * 8 + s) * 128 + (((u ^ (s & 3)) << 5) | (h << 4))));
+  }
+}
+template <int kHalf>
+__device__ __forceinline__ void cv_proc_mn(const float (&v)[32], uint32_t hb, uint32_t lb, int cw, int lane) {
+  const int q = lane >> 3, u = (lane >> 1) & 3, h = lane & 1, kg = u ^ q;
+  constexpr int i0 = kHalf * 2;
+  uint32_t h0[4], l0[4], h1[4], l1[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    split_pack(v[(2 * e) * 4 + i0], v[(2 * e + 1) * 4 + i0], h0[e], l0[e]);
+    split_pack(v[(2 * e) * 4 + i0 + 1], v[(2 * e + 1) * 4 + i0 + 1], h1[e], l1[e]);
+  }
+  uint32_t fh[4], fl[4], sh[4], sl[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    fh[e] = h ? h1[e] : h0[e]; fl[e] = h ? l1[e] : l0[e];
+    sh[e] = h ? h0[e] : h1[e]; sl[e] = h ? l0[e] : l1[e];
+  }
+  // row within the tile = cw*32 + u*8 + h*4 + i'  ->  atom (cw*4 + u), row-in-atom h*4 + i'
+  const uint32_t base = (uint32_t)((cw * 4 + u) * 512 + ((kg ^ (2 * h + kHalf)) << 4));
+  const uint32_t first = base + (uint32_t)((h * 4 + i0 + h) * 64), second = base + (uint32_t)((h * 4 + i0 + 1 - h) * 64);
+  sts128(hb + first, fh);
+  sts128(lb + first, fl);
+  sts128(hb + second, sh);
+  sts128(lb + second, sl);
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int kHi, int kLo, bool kTiming, bool kHybrid>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                         const PairParams p) {
@@ -240,6 +340,9 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn_major << 15) |
                              ((uint32_t)p.b_mn_major << 16) | ((uint32_t)((2 * PBN) >> 3) << 17) |
                              ((uint32_t)(256 >> 4) << 24);
+      // kind::f16, BF16 x BF16 -> FP32, both operands K-major, M = 256, N = 256
+      const uint32_t idesc_bf = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * PBN) >> 3) << 17) |
+                                ((uint32_t)(256 >> 4) << 24);
       const uint32_t a_lbo = p.a_mn_major ? 4096 : 16, b_lbo = p.b_mn_major ? 4096 : 16;
       const uint32_t a_sbo = p.a_mn_major ? 512 : 1024, b_sbo = p.b_mn_major ? 512 : 1024;
       const uint32_t a_lt = p.a_mn_major ? 1 : 2, b_lt = p.b_mn_major ? 1 : 2;
@@ -251,8 +354,8 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
       Segment s;
       for (WorkIter w(p, cluster, nclusters, num_k); w.next(s);) {
         for (int kb = s.kb0; kb < s.kb1; ++kb) {
-          const bool chunk_start = ((kb - s.kb0) % kChunk) == 0;
-          const bool chunk_end = ((kb - s.kb0 + 1) % kChunk) == 0 || kb == s.kb1 - 1;
+          const bool chunk_start = ((kb - s.kb0) % p.chunk) == 0;
+          const bool chunk_end = ((kb - s.kb0 + 1) % p.chunk) == 0 || kb == s.kb1 - 1;
           if (chunk_start) {
             const long long tw = MDB_T0();
             mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1);   // both CTAs drained this accumulator
@@ -267,6 +370,20 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
           if (elect_one()) {
             const uint32_t a_hi = smem_u32(smem + hi.slot * S::SLOT_BYTES), b_hi = a_hi + S::A_BYTES;
             const uint32_t a_lo = smem_u32(lo_ring + lo.slot * S::SLOT_BYTES), b_lo = a_lo + S::A_BYTES;
+            if (kHybrid) {
+              // raw x raw in TF32, then the two cross terms on the converters' K-major BF16 tiles:
+              // lo slot = [A hb | A lb | B hb | B lb], 8 KB each
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k)
+                umma_tf32_pair(tmem_d, make_desc(a_hi + k * a_kstep, a_lbo, a_sbo, a_lt),
+                               make_desc(b_hi + k * b_kstep, b_lbo, b_sbo, b_lt), idesc, !(chunk_start && k == 0));
+              const uint32_t a_hb = a_lo, a_lb = a_lo + 8192, b_hb = a_lo + 16384, b_lb = a_lo + 24576;
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                umma_bf16_pair(tmem_d, make_desc(a_lb + k * 32, 16, 512, 4), make_desc(b_hb + k * 32, 16, 512, 4), idesc_bf, 1);
+                umma_bf16_pair(tmem_d, make_desc(a_hb + k * 32, 16, 512, 4), make_desc(b_lb + k * 32, 16, 512, 4), idesc_bf, 1);
+              }
+            } else {
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t da_hi = make_desc(a_hi + k * a_kstep, a_lbo, a_sbo, a_lt);
@@ -276,6 +393,7 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
               umma_tf32_pair(tmem_d, da_lo, db_hi, idesc, !(chunk_start && k == 0));
               umma_tf32_pair(tmem_d, da_hi, db_lo, idesc, 1);
               umma_tf32_pair(tmem_d, da_hi, db_hi, idesc, 1);
+            }
             }
             umma_commit_pair(&lo_empty[lo.slot]);
             umma_commit_pair(&hi_empty[hi.slot]);
@@ -294,7 +412,10 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     }
   } else if (warp >= 4 + kPairEpiWarps) {
     // ===================================== converters (both CTAs) ============================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    // hybrid: 72 (two 32-register tile fragments in flight); the shares still balance exactly:
+    // released 4*32*88 + 128*56 = 18432 = requested 256*72
+    if (kHybrid) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     constexpr int kConv = kPairConvWarps * 32;                     // 128 threads
     const int t = threadIdx.x - (4 + kPairEpiWarps) * 32;
     Ring hi, lo;
@@ -311,6 +432,21 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
         const long long tc0 = MDB_T0();
         const uint32_t src = smem_u32(smem + hi.slot * S::SLOT_BYTES);
         const uint32_t dst = smem_u32(lo_ring + lo.slot * S::SLOT_BYTES);
+        if (kHybrid) {
+          const int cw = t >> 5;
+          const uint32_t src_b = src + S::A_BYTES;
+          const uint32_t a_hb = dst, a_lb = dst + 8192, b_hb = dst + 16384, b_lb = dst + 24576;
+          float va[32], vb[32];
+          // loads of the B tile are issued between the two halves of the A tile's conversion
+          if (p.a_mn_major) { cv_load_mn<0>(va, src, cw, lane); cv_load_mn<1>(va, src, cw, lane); }
+          else { cv_load_k<0>(va, src, cw, lane); cv_load_k<1>(va, src, cw, lane); }
+          if (p.a_mn_major) cv_proc_mn<0>(va, a_hb, a_lb, cw, lane); else cv_proc_k<0>(va, a_hb, a_lb, cw, lane);
+          if (p.b_mn_major) cv_load_mn<0>(vb, src_b, cw, lane); else cv_load_k<0>(vb, src_b, cw, lane);
+          if (p.a_mn_major) cv_proc_mn<1>(va, a_hb, a_lb, cw, lane); else cv_proc_k<1>(va, a_hb, a_lb, cw, lane);
+          if (p.b_mn_major) cv_load_mn<1>(vb, src_b, cw, lane); else cv_load_k<1>(vb, src_b, cw, lane);
+          if (p.b_mn_major) { cv_proc_mn<0>(vb, b_hb, b_lb, cw, lane); cv_proc_mn<1>(vb, b_hb, b_lb, cw, lane); }
+          else { cv_proc_k<0>(vb, b_hb, b_lb, cw, lane); cv_proc_k<1>(vb, b_hb, b_lb, cw, lane); }
+        } else {
         constexpr int kVecs = S::SLOT_BYTES / 16 / kConv;          // 16 float4 per thread
         constexpr int kBatch = 4, kBatches = kVecs / kBatch;
         // software pipeline: the loads of batch b+1 are in flight while batch b is converted and stored
@@ -341,6 +477,7 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
                          "f"(e[0]), "f"(e[1]), "f"(e[2]), "f"(e[3])
                          : "memory");
           }
+        }
         }
         MDB_TACC(t_work, tc0);
         const long long td = MDB_T0();
@@ -379,8 +516,14 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
       float sum[128];
 #pragma unroll
       for (int j = 0; j < 128; ++j) sum[j] = 0.f;
-      const int num_chunks = (s.kb1 - s.kb0 + kChunk - 1) / kChunk;
+      const int num_chunks = (s.kb1 - s.kb0 + p.chunk - 1) / p.chunk;
       for (int ch = 0; ch < num_chunks; ++ch) {
+        // The tensor core TRUNCATES the fp32 accumulator after every instruction: a chain of n instructions loses
+        // ~0.5 ulp per step, always toward zero, and the running sum grows towards its final value r, so the
+        // expected loss is proportional to r itself: E[loss | r] ~ rz_gain * n * r.  The promotion adds it back
+        // with the multiply of an FMA (no extra instruction); what remains is the zero-mean part of the error.
+        const int kbs = min(p.chunk, s.kb1 - s.kb0 - ch * p.chunk);
+        const float comp = 1.f + p.rz_gain * (float)(kbs * (kHybrid ? 8 : 12));
         const long long tw = MDB_T0();
         mbar_wait(&tmem_full[acc], acc_phase);
         MDB_TACC(w_full, tw);
@@ -392,7 +535,7 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
           MDB_TMEM_LD32(taddr, r);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sum[c * 32 + j] = __fadd_rn(sum[c * 32 + j], __uint_as_float(r[j]));
+          for (int j = 0; j < 32; ++j) sum[c * 32 + j] = __fmaf_rn(__uint_as_float(r[j]), comp, sum[c * 32 + j]);
         }
         tcgen05_fence_before();
         __syncwarp();

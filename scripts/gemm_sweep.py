@@ -14,7 +14,7 @@ import minidiff_b200.backend as Bk  # noqa: E402
 from minidiff_b200.backend import functions as F  # noqa: E402
 from minidiff_b200.backend._lib import check, lib  # noqa: E402
 
-KNOB = dict(raster=0, group=1, hint_a=2, hint_b=3, hint_c=4, streamk=5, l2=6)
+KNOB = dict(raster=0, group=1, hint_a=2, hint_b=3, hint_c=4, streamk=5, l2=6, split=8, chunk=9)
 Bsz = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 rounds = int(sys.argv[2]) if len(sys.argv) > 2 else 7
 only = sys.argv[3].split(",") if len(sys.argv) > 3 else None
@@ -73,6 +73,10 @@ variants = [("old_r0g8", dict(raster=0, group=8, hint_a=0, hint_b=0, hint_c=0, s
 if os.environ.get("SWEEP") == "flags":
     # kernel-flag A/B (mdb_gemm_tune bits) instead of planner knobs
     variants = [("base", dict(_flags=4 | 32)), ("lo_rounded", dict(_flags=32)), ("base2", dict(_flags=4 | 32))]
+if os.environ.get("SWEEP") == "split":
+    # operand split A/B: 3xTF32 vs TF32 + 2 BF16 cross terms
+    variants = [("3xtf32 c4", dict(split=0, chunk=4)), ("3xtf32 c2", dict(split=0, chunk=2)), ("hybrid c4", dict(split=1, chunk=4)),
+                ("hybrid c2", dict(split=1, chunk=2)), ("hybrid c1", dict(split=1, chunk=1))]
 check(lib.mdb_gemm_tune(4 | 32))
 for name, (M, K, N), ta, tb in shapes:
     if only and name not in only:

@@ -328,12 +328,12 @@ def _gemm_paths(reset=False):
                 pair_streamk=int(counts[4]))
 
 
-def _close_rms(got, want, what):
+def _close_rms(got, want, what, atol=1e-5):
     """north_star tolerance for reductions / GEMMs, rtol 1e-4 / atol 1e-5, with the atol scaled by
     the rms of the reference values (the gradients here are ~1e-5..1e-2, not ~1)."""
     want = np.asarray(want)
     rms = float(np.sqrt(np.mean(np.square(want.astype(np.float64)))))
-    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5 * rms, err_msg=what)
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=atol * rms, err_msg=what)
 
 
 _CASES = {}
@@ -383,6 +383,35 @@ def test_c4_baseline_dims_vs_oracle_on_the_pair_kernel(md):
         _close_rms(grads[i], want["grads"][i], f"grad {i} vs oracle")
         _close_rms(grads[i], truth["grads"][i], f"grad {i} vs float64")
         _close_rms(ps[i].as_numpy(), want["params"][i], f"param {i} vs oracle")
+
+
+def test_c4_baseline_dims_with_the_fast_gemm_split(md):
+    """Same step with the opt-in "fast" operand split (one TF32 MMA + two BF16 cross-term MMAs per product,
+    backend.set_matmul_split): against the oracle and float64 at rtol 1e-4 / atol 3e-5*rms -- three times the
+    default's atol, which is why the split is opt-in -- and the gradients' rms error stays below 4e-6 of their rms."""
+    from minidiff_b200.backend._lib import check, lib
+
+    X, Y, ps_np, want, truth = _c4_baseline_case()
+    check(lib.mdb_gemm_config(2))
+    check(lib.mdb_gemm_tune(4 | 32))
+    import minidiff_b200.backend as device_backend      # process-wide switch of the C-ABI library, either engine
+
+    device_backend.set_matmul_split("fast")
+    _gemm_paths(reset=True)
+    try:
+        loss, grads, ps = run_c4(md, X, Y, ps_np)
+    finally:
+        device_backend.set_matmul_split("3xtf32")
+        check(lib.mdb_gemm_tune(4))
+        check(lib.mdb_gemm_config(0))
+    paths = _gemm_paths()
+    assert paths["pair"] + paths["pair_streamk"] == 8, paths
+    close(loss, want["loss"], rtol=1e-5)
+    for i in range(6):
+        _close_rms(grads[i], want["grads"][i], f"grad {i} vs oracle", atol=3e-5)
+        _close_rms(grads[i], truth["grads"][i], f"grad {i} vs float64", atol=3e-5)
+        t = np.asarray(truth["grads"][i], dtype=np.float64)
+        assert np.sqrt(np.mean((grads[i] - t) ** 2)) < 4e-6 * np.sqrt(np.mean(t ** 2)), i
 
 
 def test_c5_full_baseline_config_vs_oracle_and_float64(md):

@@ -165,6 +165,128 @@ def knobs(B):
 SK_SHAPES = [(1300, 4096, 1500), (2304, 2048, 2304), (2816, 1024, 2816), (300, 8200, 520), (520, 640, 4100)]
 
 
+@pytest.fixture
+def fast_split(B):
+    """The opt-in "fast" operand split of the CTA-pair kernel (B.set_matmul_split("fast"): one TF32 MMA + the two
+    cross terms as BF16 MMAs), pair kernel forced."""
+    from minidiff_b200.backend._lib import check, lib
+
+    check(lib.mdb_gemm_config(2))
+    check(lib.mdb_gemm_tune(4 | 32))
+    B.set_matmul_split("fast")
+    yield
+    B.set_matmul_split("3xtf32")
+    check(lib.mdb_gemm_tune(4))
+    check(lib.mdb_gemm_config(0))
+
+
+@pytest.mark.parametrize("layout", ["NN", "NT", "TN", "TT"])
+def test_operand_splits_accuracy_against_float64(B, layout):
+    """Both operand splits against float64 on inputs spanning e^+-8 in magnitude.  Default (3xTF32 with the
+    accumulator-truncation compensation): rms error < 0.8e-6 of the result's rms (measured 0.53e-6; NumPy sgemm
+    0.34e-6).  Fast split: < 2e-6 (measured 1.36e-6), i.e. ~2.6x the default and ~400x better than plain TF32."""
+    from minidiff_b200.backend._lib import check, lib
+
+    M, K, N = 768, 2048, 512
+    rng = np.random.default_rng(11)
+    a = (rng.standard_normal((M, K)) * np.exp(rng.uniform(-8, 8, (M, K)))).astype(np.float32)
+    b = (rng.standard_normal((K, N)) * np.exp(rng.uniform(-8, 8, (K, N)))).astype(np.float32)
+    da = B.asarray(a) if layout[0] == "N" else B.asarray(np.ascontiguousarray(a.T)).T
+    db = B.asarray(b) if layout[1] == "N" else B.asarray(np.ascontiguousarray(b.T)).T
+    truth = a.astype(np.float64) @ b.astype(np.float64)
+    rms = np.sqrt(np.mean(truth ** 2))
+    check(lib.mdb_gemm_config(2))
+    check(lib.mdb_gemm_tune(4 | 32))
+    errs = {}
+    try:
+        for mode, atol in (("3xtf32", 1e-5), ("fast", 2e-5)):
+            B.set_matmul_split(mode)
+            got = B.matmul(da, db).numpy()
+            assert np.allclose(got, truth, rtol=1e-4, atol=atol * rms), mode
+            errs[mode] = np.sqrt(np.mean((got - truth) ** 2)) / rms
+    finally:
+        B.set_matmul_split("3xtf32")
+        check(lib.mdb_gemm_tune(4))
+        check(lib.mdb_gemm_config(0))
+    assert errs["3xtf32"] < 0.8e-6 and errs["fast"] < 2e-6, errs
+
+
+def test_truncation_compensation_halves_the_3xtf32_error(B):
+    """The tensor core truncates its fp32 accumulator after every instruction; the promotion step adds the expected
+    loss back (RZ_GAIN knob).  Without it the rms error is ~2.3x larger."""
+    from minidiff_b200.backend._lib import check, lib
+
+    a, b, da, db = operands(B, 512, 2048, 512, "NN", seed=21)
+    truth = a.astype(np.float64) @ b.astype(np.float64)
+    rms = np.sqrt(np.mean(truth ** 2))
+    check(lib.mdb_gemm_config(2))
+    errs = {}
+    try:
+        for kernel, tune in (("pair", 4 | 32), ("single", 4 | 16)):
+            check(lib.mdb_gemm_tune(tune))
+            for gain in (0, -1):
+                check(lib.mdb_gemm_knob(10, gain))
+                errs[kernel, gain] = np.sqrt(np.mean((B.matmul(da, db).numpy() - truth) ** 2)) / rms
+    finally:
+        check(lib.mdb_gemm_knob(10, -1))
+        check(lib.mdb_gemm_tune(4))
+        check(lib.mdb_gemm_config(0))
+    for kernel in ("pair", "single"):
+        assert errs[kernel, -1] < 0.6 * errs[kernel, 0], errs
+        assert errs[kernel, -1] < 0.8e-6, errs
+
+
+@pytest.mark.parametrize("layout", ["NN", "NT", "TN", "TT"])
+@pytest.mark.parametrize("M,K,N", [(256, 512, 384), (129, 200, 130), (1000, 777, 555), (2048, 1024, 1536), (300, 260, 272)])
+def test_fast_split_every_layout_and_ragged_extents(B, fast_split, M, K, N, layout):
+    """The fast split transposes MN-major raw tiles in registers into K-major BF16 tiles: every layout combination,
+    ragged M / N / K (TMA zero fill), against float64 at rtol 1e-4 / atol 2e-5 x sqrt(K) (twice the default's atol)."""
+    a, b, da, db = operands(B, M, K, N, layout, seed=M + K + N)
+    got = B.matmul(da, db).numpy()
+    truth = a.astype(np.float64) @ b.astype(np.float64)
+    np.testing.assert_allclose(got, truth, rtol=1e-4, atol=2e-5 * np.sqrt(K))
+    assert np.sqrt(np.mean((got - truth) ** 2)) < 2.5e-6 * np.sqrt(K)
+
+
+def test_fast_split_handles_huge_and_tiny_magnitudes(B, fast_split):
+    """BF16 has fp32's exponent range, so the cross terms neither overflow nor flush where 3xTF32 does not:
+    operands near FLT_MAX / FLT_MIN scale (products kept finite) agree with float64."""
+    M, K, N = 256, 256, 256
+    rng = np.random.default_rng(5)
+    a = (rng.standard_normal((M, K)) * 1e30).astype(np.float32)
+    b = (rng.standard_normal((K, N)) * 1e-32).astype(np.float32)
+    a[0, :] = np.float32(3.4e38)                   # rounds to +inf in BF16 unless the conversion saturates
+    b[:, 0] = np.float32(2e-38)
+    truth = a.astype(np.float64) @ b.astype(np.float64)
+    got = B.matmul(B.asarray(a), B.asarray(b)).numpy()
+    assert np.isfinite(got).all()
+    assert np.allclose(got, truth, rtol=1e-4, atol=2e-5 * np.sqrt(np.mean(truth ** 2)))
+
+
+def test_fast_split_stream_k_and_fused_epilogue(B, fast_split):
+    """Stream-K hand-over and the fused bias/relu/mask epilogue are shared code: same results as the data-parallel,
+    unfused launches of the same split, bit for bit where the arithmetic is the same."""
+    from minidiff_b200.backend import functions as F
+    from minidiff_b200.backend._lib import check, lib
+
+    M, K, N = 2304, 2048, 2304                       # 81 tiles on 74 clusters: a partial last wave
+    a, b, da, db = operands(B, M, K, N, "NN", seed=9)
+    truth = a.astype(np.float64) @ b.astype(np.float64)
+    bias = np.random.default_rng(1).standard_normal(N).astype(np.float32)
+    try:
+        check(lib.mdb_gemm_knob(5, 0))
+        dp = B.matmul(da, db).numpy()
+        fused = F._gemm_fused(da, db, bias=B.asarray(bias), relu=True).numpy()     # same (data-parallel) summation order
+        check(lib.mdb_gemm_knob(5, 1))
+        sk = B.matmul(da, db).numpy()
+    finally:
+        check(lib.mdb_gemm_knob(5, -1))
+    np.testing.assert_allclose(dp, truth, rtol=1e-4, atol=2e-5 * np.sqrt(K))
+    np.testing.assert_allclose(sk, dp, rtol=1e-4, atol=5e-6 * np.sqrt(K))
+    plain = dp + bias
+    assert np.array_equal(fused, np.where(plain > 0, plain, np.float32(0)))
+
+
 @pytest.mark.parametrize("layout", ["NN", "NT", "TN", "TT"])
 @pytest.mark.parametrize("M,K,N", SK_SHAPES)
 def test_stream_k_split_matches_float64(B, knobs, M, K, N, layout):
