@@ -57,7 +57,25 @@ struct RedParams {
   // deposit its partial folds all partials (fixed order: deterministic) and writes the result.
   unsigned int* tickets;   // self-resetting arrival counters, or nullptr for the two-launch scheme
   float* final_dst;        // where the last CTA writes (dst is the partial buffer)
+  // column sums: `csize` CTAs that share a column tile form a thread-block cluster along the split axis
+  // and fold their sums through distributed shared memory; `nparts` = nsplit / csize partial rows remain
+  uint32_t csize, nparts;
 };
+
+__device__ __forceinline__ uint32_t red_cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void red_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float red_ld_dsmem(const float* local, uint32_t rank) {
+  float v;
+  asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %1, %2;\n\tld.shared::cluster.f32 %0, [ra];\n\t}"
+               : "=f"(v) : "r"((uint32_t)__cvta_generic_to_shared(local)), "r"(rank) : "memory");
+  return v;
+}
 
 template <int OP, int NIN, int VEC>
 __device__ __forceinline__ void load_apply(const RedParams& p, uint32_t i2, uint32_t i1,
@@ -359,13 +377,39 @@ __global__ void __launch_bounds__(256, (NIN == 2 && F0 == FV && F1 == FV) ? 5 : 
 #pragma unroll
   for (int j = 0; j < 4; ++j) sm[ty][tx][j] = acc[j];
   __syncthreads();
-  if (ty == 0 && active) {
+  if (p.csize > 1) {
+    // cluster of csize CTAs (same column tile, consecutive row ranges): fold through distributed shared memory,
+    // in rank order, on the rank-0 CTA -- csize times fewer partial rows, no second pass over them when nparts == 1
+    __shared__ float cs[128];
+    if (ty == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a = sm[0][tx][j];
+#pragma unroll
+        for (int t = 1; t < 8; ++t) a = red_combine<RED>(a, sm[t][tx][j]);
+        cs[tx * 4 + j] = a;                                   // columns past I hold the identity
+      }
+    }
+    red_cluster_sync();
+    const uint32_t crank = red_cluster_ctarank();
+    if (crank == 0 && threadIdx.x < 128) {
+      float a = cs[threadIdx.x];
+      for (uint32_t r = 1; r < p.csize; ++r) a = red_combine<RED>(a, red_ld_dsmem(&cs[threadIdx.x], r));
+      const uint32_t c = blockIdx.x * 128 + threadIdx.x;
+      if (c < p.I) {
+        if (p.to_partial) p.dst[((int64_t)o2 * p.nparts + split / p.csize) * p.I + c] = a;
+        else final_store(p, p.dst + (int64_t)o2 * p.os2 + c, a);
+      }
+    }
+    red_cluster_sync();                                       // peers stay resident until rank 0 has read them
+    if (crank != 0) return;
+  } else if (ty == 0 && active) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float a = sm[0][tx][j];
 #pragma unroll
       for (int t = 1; t < 8; ++t) a = red_combine<RED>(a, sm[t][tx][j]);
-      if (p.to_partial) p.dst[((int64_t)o2 * p.nsplit + split) * p.I + col + j] = a;
+      if (p.to_partial) p.dst[((int64_t)o2 * p.nparts + split) * p.I + col + j] = a;
       else final_store(p, p.dst + (int64_t)o2 * p.os2 + col + j, a);
     }
   }
@@ -374,7 +418,7 @@ __global__ void __launch_bounds__(256, (NIN == 2 && F0 == FV && F1 == FV) ? 5 : 
   __threadfence();
   __syncthreads();
   const unsigned int tile = o2 * gridDim.x + blockIdx.x;
-  if (threadIdx.x == 0) s_last = atomicAdd(&p.tickets[tile], 1u) == p.nsplit - 1;
+  if (threadIdx.x == 0) s_last = atomicAdd(&p.tickets[tile], 1u) == p.nparts - 1;
   __syncthreads();
   if (!s_last) return;
   // last CTA of this column tile: fold the partial rows of all splits, 8 row groups then the tree
@@ -383,8 +427,8 @@ __global__ void __launch_bounds__(256, (NIN == 2 && F0 == FV && F1 == FV) ? 5 : 
 #pragma unroll
   for (int j = 0; j < 4; ++j) t4[j] = red_identity<RED>();
   if (active) {
-    for (uint32_t k = ty; k < p.nsplit; k += 8) {
-      const float4 v = __ldcg((const float4*)(p.dst + ((int64_t)o2 * p.nsplit + k) * p.I + col));
+    for (uint32_t k = ty; k < p.nparts; k += 8) {
+      const float4 v = __ldcg((const float4*)(p.dst + ((int64_t)o2 * p.nparts + k) * p.I + col));
       t4[0] = red_combine<RED>(t4[0], v.x); t4[1] = red_combine<RED>(t4[1], v.y);
       t4[2] = red_combine<RED>(t4[2], v.z); t4[3] = red_combine<RED>(t4[3], v.w);
     }
@@ -584,17 +628,32 @@ static bool launch_row_forms(const int (&f)[2], dim3 grid, const RedParams& p) {
     return false;
   }
 }
+// plain launch, or -- when p.csize > 1 -- clusters of csize CTAs along the split axis (grid.y)
+template <typename K>
+static void launch_col_kernel(K kern, dim3 grid, const RedParams& p) {
+  if (p.csize <= 1) {
+    kern<<<grid, 256, 0, g_stream>>>(p);
+    return;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(256, 1, 1); cfg.dynamicSmemBytes = 0; cfg.stream = g_stream;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 1; attr.val.clusterDim.y = p.csize; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, p);
+}
 template <int OP, int NIN, int RED>
 static bool launch_col_forms(const int (&f)[2], dim3 grid, const RedParams& p) {
   if constexpr (NIN == 1) {
-    red_col_f32<OP, 1, RED, FV, FV><<<grid, 256, 0, g_stream>>>(p);
+    launch_col_kernel(red_col_f32<OP, 1, RED, FV, FV>, grid, p);
     return true;
   } else if constexpr (NIN == 2) {
-    if (f[0] == FV && f[1] == FV) red_col_f32<OP, 2, RED, FV, FV><<<grid, 256, 0, g_stream>>>(p);
-    else if (f[0] == FV && f[1] == FS) red_col_f32<OP, 2, RED, FV, FS><<<grid, 256, 0, g_stream>>>(p);
-    else if (f[0] == FS && f[1] == FV) red_col_f32<OP, 2, RED, FS, FV><<<grid, 256, 0, g_stream>>>(p);
-    else if (f[0] == FV && f[1] == FK) red_col_f32<OP, 2, RED, FV, FK><<<grid, 256, 0, g_stream>>>(p);
-    else if (f[0] == FK && f[1] == FV) red_col_f32<OP, 2, RED, FK, FV><<<grid, 256, 0, g_stream>>>(p);
+    if (f[0] == FV && f[1] == FV) launch_col_kernel(red_col_f32<OP, 2, RED, FV, FV>, grid, p);
+    else if (f[0] == FV && f[1] == FS) launch_col_kernel(red_col_f32<OP, 2, RED, FV, FS>, grid, p);
+    else if (f[0] == FS && f[1] == FV) launch_col_kernel(red_col_f32<OP, 2, RED, FS, FV>, grid, p);
+    else if (f[0] == FV && f[1] == FK) launch_col_kernel(red_col_f32<OP, 2, RED, FV, FK>, grid, p);
+    else if (f[0] == FK && f[1] == FV) launch_col_kernel(red_col_f32<OP, 2, RED, FK, FV>, grid, p);
     else return false;
     return true;
   } else {
@@ -607,6 +666,7 @@ static int launch_fast_red(const RedPlan& pl, RedParams p, int vec, float* out, 
                            float divisor) {
   p.accumulate = accumulate; p.divisor = divisor;
   p.tickets = nullptr; p.final_dst = nullptr;
+  p.csize = 1; p.nparts = 1;
   int form[2];
   static const bool no_forms = getenv("MDB_RED_GENERIC") != nullptr;       // A/B switch for measurements
   const bool forms_ok = !no_forms && vec == 4 && classify_forms(pl, p, NIN, form);
@@ -688,38 +748,66 @@ static int launch_fast_red(const RedPlan& pl, RedParams p, int vec, float* out, 
   if ((int64_t)nsplit * I * O2 >= (int64_t(1) << 31)) nsplit = 1;
   uint32_t seg = (uint32_t)((R + nsplit - 1) / nsplit);
   nsplit = (uint32_t)((R + seg - 1) / seg);
-  p.seg = seg; p.nsplit = nsplit;
+  // f32 form kernels with >= 8 splits: clusters of 4..8 CTAs along the split axis fold their column sums through
+  // distributed shared memory (fixed rank order), so only nsplit / csize partial rows reach global memory; the
+  // cluster leaders of a column tile take a ticket and the last one folds those rows -- ONE launch.  Measured on
+  // 2^26 elements (two launches: 50.3 us = 0.81 of the HBM peak): clusters over the SAME 3.5 k short CTAs 60 us (a
+  // cluster holds its slots until its slowest member is done, at every one of 4 wave boundaries); one resident
+  // wave of long CTAs 47.7-48.6 us = 0.85.  MDB_RED_COL_CLUSTER=0 two launches, 1 short CTAs, 2 (default) one wave.
+  static const int col_cluster = getenv("MDB_RED_COL_CLUSTER") ? atoi(getenv("MDB_RED_COL_CLUSTER")) : 2;
+  uint32_t csize = 1;
+  if (col_cluster && vec == 4 && forms_ok && nsplit >= 8 && gx * O2 <= kTickets) {
+    csize = 8;
+    if (col_cluster == 2) {
+      // ONE resident wave of long CTAs (clusters wait for their slowest member: short CTAs in several waves lose
+      // slots at every cluster boundary): the largest split count that fits the resident slots and has a
+      // cluster-sized divisor
+      const int64_t slots = (int64_t)g_sm_count * 6;
+      const int64_t nmax = std::min<int64_t>(std::max<int64_t>(8, slots / (gx * O2)), std::max<int64_t>(8, R / 64));
+      nsplit = 8;                                        // < 16 splits fit: 8 (one cluster per tile, no partial rows)
+      for (int64_t n = nmax; nmax >= 16 && n >= nmax - 7; --n) {
+        uint32_t c = 0;
+        for (uint32_t d = 8; d >= 4; --d) if (n % d == 0) { c = d; break; }
+        if (c) { nsplit = (uint32_t)n; csize = c; break; }
+      }
+    } else {
+      nsplit = (nsplit + 7) / 8 * 8;                     // trailing CTAs may own no rows: they contribute the identity
+    }
+    seg = (uint32_t)((R + nsplit - 1) / nsplit);
+  }
+  const uint32_t nparts = nsplit / csize;
+  p.seg = seg; p.nsplit = nsplit; p.csize = csize; p.nparts = nparts;
   TempBuf tmp;
-  if (nsplit > 1) {
-    MDB_TRY(tmp.alloc((size_t)O2 * nsplit * I * sizeof(float)));
+  if (nparts > 1) {
+    MDB_TRY(tmp.alloc((size_t)O2 * nparts * I * sizeof(float)));
     p.dst = (float*)tmp.ptr; p.to_partial = 1;
   } else {
     p.dst = out; p.to_partial = 0;
   }
   dim3 grid((unsigned)gx, nsplit, (unsigned)O2);
-  // The single-launch scheme is NOT used for column sums: measured 52.8 vs 50.6 us on (8192,8192) --
-  // the fence + ticket in each of the 3.5 k short CTAs costs more than the 5 us second launch it saves
-  // (for full sums it replaces a 9 us single-CTA pass: 51.4 -> 47.5 us).  MDB_RED_COL_TICKETS=1 turns
-  // it on for measurements.
+  // Per-CTA tickets are NOT used for column sums: measured 52.8 vs 50.6 us on (8192,8192) -- the fence + ticket in
+  // each of the 3.5 k short CTAs costs more than the 5 us second launch it saves.  With clusters only the leaders
+  // (1 in 8) take one.  MDB_RED_COL_TICKETS=1 turns the per-CTA scheme on for measurements.
   static const bool col_tickets = getenv("MDB_RED_COL_TICKETS") != nullptr;
-  if (col_tickets && vec == 4 && forms_ok && nsplit > 1 && gx * O2 <= kTickets) {
+  if ((col_tickets || csize > 1) && vec == 4 && forms_ok && nparts > 1 && gx * O2 <= kTickets) {
     p.tickets = ticket_pool();
     p.final_dst = out;
   }
   bool used_forms = false;
   if (vec == 4) {
     if (forms_ok && (used_forms = launch_col_forms<OP, NIN, RED>(form, grid, p))) {}
+    else if (csize > 1) return MDB_EINVAL;               // unreachable: classify_forms() admits only launchable forms
     else if (NIN > 1 && late) red_col<OP, NIN, RED, 4, (NIN > 1)><<<grid, 256, 0, g_stream>>>(p);
     else red_col<OP, NIN, RED, 4><<<grid, 256, 0, g_stream>>>(p);
   } else {
     red_col<OP, NIN, RED, 1><<<grid, 256, 0, g_stream>>>(p);
   }
   MDB_CHECK_LAUNCH();
-  if (nsplit > 1 && !(used_forms && p.tickets)) {
+  if (nparts > 1 && !(used_forms && p.tickets)) {
     RedParams q = p;
     q.in[0].ptr = tmp.ptr; q.in[0].kind = K_F32; q.in[0].s0 = 1;
-    q.in[0].s1 = (int32_t)I; q.in[0].s2 = (int32_t)((int64_t)nsplit * I);
-    q.L = nsplit; q.seg = nsplit; q.nsplit = 1; q.dst = out; q.to_partial = 0;
+    q.in[0].s1 = (int32_t)I; q.in[0].s2 = (int32_t)((int64_t)nparts * I);
+    q.L = nparts; q.seg = nparts; q.nsplit = 1; q.csize = 1; q.nparts = 1; q.dst = out; q.to_partial = 0;
     const bool v4 = (vec == 4);  // partial rows are 16B aligned iff I % 4 == 0 (true when vec == 4)
     dim3 grid2((unsigned)gx, 1, (unsigned)O2);
     if (v4) red_col<MDB_OP_COPY, 1, RED, 4><<<grid2, 256, 0, g_stream>>>(q);
