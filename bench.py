@@ -45,7 +45,7 @@ sys.path.insert(0, ROOT)
 
 # ncu --set full capture of one C4 step at N=1 (profiles/r02_ncu_mlp_step_gemm.md): DRAM bytes per GEMM
 # launch, and the algorithmic figure beside it (each operand read once + C written once, 8 GEMMs/step)
-GEMM_TRAFFIC_BYTES_PER_LAUNCH = 2.851e9
+GEMM_TRAFFIC_BYTES_PER_LAUNCH = 3.656e9
 GEMM_ALGORITHMIC_BYTES_PER_LAUNCH = (
     # fwd1, fwd2, fwd3 (X@W), dW3, dh2, dW2, dh1, dW1 at B=65536, D=(1024,4096,4096,1024)
     sum(4.0 * (m * k + k * n + m * n) for m, k, n in [
@@ -58,8 +58,9 @@ C2_TRAFFIC_SRC = ("dram__bytes_read.sum + dram__bytes_write.sum over the 13 laun
                   "profiles/r01_c2_launches_v3.csv (below the algorithmic 4.295e9: part of each output is still "
                   "in the 126 MB L2 when the next op reads it)")
 GEMM_TRAFFIC_SRC = ("dram__bytes_read.sum + dram__bytes_write.sum averaged over the 8 GEMM launches of one C4 step "
-                    "(ncu --set full, profiles/r02_ncu_mlp_step_gemm.md)")
-C3_TRAFFIC_BYTES_PER_LAUNCH = 2.571e9
+                    "(ncu --set full, profiles/r02_ncu_mlp_step_gemm.md; captures of the same code on different "
+                    "boxes gave 2.85-3.68 GB: what the L2 keeps between waves varies)")
+C3_TRAFFIC_BYTES_PER_LAUNCH = 3.055e9
 C3_TRAFFIC_SRC = ("dram__bytes_read.sum + dram__bytes_write.sum per 8192^3 launch of the shipped pair kernel "
                   "(ncu --set full, profiles/r02_ncu_c3_gemm.md)")
 GLOBAL_BATCH = int(os.environ.get("MDB_BENCH_GLOBAL_BATCH", 65536))   # override for experiments only (scripts/dp_contention.sh)

@@ -348,7 +348,8 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
           MDB_TMEM_LD32(taddr, r);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sum[c * 32 + j] = __fmaf_rn(__uint_as_float(r[j]), comp, sum[c * 32 + j]);
+          for (int j = 0; j < 32; ++j)   // a chain sum with zero low bits lost nothing (exact inputs, e.g. small integers): keep it exact
+            sum[c * 32 + j] = __fmaf_rn(__uint_as_float(r[j]), (r[j] & 0xFu) ? comp : 1.f, sum[c * 32 + j]);
         }
         tcgen05_fence_before();
         __syncwarp();

@@ -236,6 +236,20 @@ def test_truncation_compensation_halves_the_3xtf32_error(B):
         assert errs[kernel, -1] < 0.8e-6, errs
 
 
+def test_exactly_representable_products_stay_exact(B, force_tc):
+    """The truncation compensation must not touch sums that lost nothing: 0/1 matrices, small integers and powers
+    of two give the exact integer / dyadic results NumPy gives."""
+    rng = np.random.default_rng(2)
+    M, K, N = 384, 1024, 512
+    cases = [(np.ones((M, K), np.float32), np.ones((K, N), np.float32)),
+             (rng.integers(-9, 10, (M, K)).astype(np.float32), rng.integers(-9, 10, (K, N)).astype(np.float32)),
+             ((rng.integers(0, 2, (M, K)) * 0.25).astype(np.float32), (rng.integers(0, 2, (K, N)) * 8.0).astype(np.float32))]
+    for a, b in cases:
+        got = B.matmul(B.asarray(a), B.asarray(b)).numpy()
+        assert np.array_equal(got, a @ b)
+        assert np.array_equal(got, (a.astype(np.float64) @ b.astype(np.float64)).astype(np.float32))
+
+
 @pytest.mark.parametrize("layout", ["NN", "NT", "TN", "TT"])
 @pytest.mark.parametrize("M,K,N", [(256, 512, 384), (129, 200, 130), (1000, 777, 555), (2048, 1024, 1536), (300, 260, 272)])
 def test_fast_split_every_layout_and_ragged_extents(B, fast_split, M, K, N, layout):
