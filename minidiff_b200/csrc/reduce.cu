@@ -336,12 +336,16 @@ __global__ void __launch_bounds__(256, (NIN == 2 && F0 == FV && F1 == FV) ? 5 : 
   }
 }
 
-template <int OP, int NIN, int RED, int F0, int F1>
-__global__ void __launch_bounds__(256, (NIN == 2 && F0 == FV && F1 == FV) ? 5 : 6) red_col_f32(const RedParams p) {
-  constexpr int U = 4;
-  __shared__ float sm[8][32][4];
-  const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const uint32_t col = (blockIdx.x * 32 + tx) * 4;
+// TX = threads across a column tile (TX * 4 columns, at least one 128-B line per row); 256 / TX row lanes
+template <int OP, int NIN, int RED, int F0, int F1, int TX>
+__global__ void __launch_bounds__(256, 4) red_col_f32(const RedParams p) {
+  constexpr int TY = 256 / TX;
+  // 8 rows (float4 each) in flight per thread for single-vector forms: the one-wave cluster launch has at most
+  // 4 CTAs per SM and needs ~16 MB outstanding to cover the HBM bandwidth-delay product
+  constexpr int U = (NIN == 2 && F0 == FV && F1 == FV) ? 4 : 8;
+  __shared__ float sm[TY][TX][4];
+  const uint32_t tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  const uint32_t col = (blockIdx.x * TX + tx) * 4;
   const uint32_t split = blockIdx.y, o2 = blockIdx.z;
   const bool active = col < p.I;
   const uint32_t r0 = split * p.seg, r1 = min(r0 + p.seg, p.L);
@@ -355,13 +359,13 @@ __global__ void __launch_bounds__(256, (NIN == 2 && F0 == FV && F1 == FV) ? 5 : 
     const int64_t st0 = p.in[0].s1, st1 = NIN > 1 ? p.in[1].s1 : 0;
     const float k0 = F0 == FK ? const_of(p.in[0], (int64_t)(int32_t)o2 * p.in[0].s2) : 0.f;
     const float k1 = (NIN > 1 && F1 == FK) ? const_of(p.in[1], (int64_t)(int32_t)o2 * p.in[1].s2) : 0.f;
-    for (uint32_t r = r0 + ty; r < r1; r += 8 * U) {
+    for (uint32_t r = r0 + ty; r < r1; r += TY * U) {
       float4 x0[U], x1[U];
       float s0v[U], s1v[U];
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        if (r + u * 8 < r1) {
-          const int64_t rr = (int64_t)(r + u * 8);
+        if (r + u * TY < r1) {
+          const int64_t rr = (int64_t)(r + u * TY);
           if constexpr (F0 == FV) x0[u] = st0 ? ldg_stream4((const float4*)(q0 + rr * st0)) : __ldg((const float4*)q0);
           if constexpr (F0 == FS) s0v[u] = __ldg(q0 + rr * st0);
           if constexpr (NIN > 1 && F1 == FV) x1[u] = st1 ? ldg_stream4((const float4*)(q1 + rr * st1)) : __ldg((const float4*)q1);
@@ -369,7 +373,7 @@ __global__ void __launch_bounds__(256, (NIN == 2 && F0 == FV && F1 == FV) ? 5 : 
         }
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        if (r + u * 8 < r1)
+        if (r + u * TY < r1)
           fold4<OP, NIN, RED>(p, form_value<F0>(x0[u], F0 == FS ? s0v[u] : k0),
                               form_value<F1>(x1[u], F1 == FS ? s1v[u] : k1), acc);
     }
@@ -380,22 +384,22 @@ __global__ void __launch_bounds__(256, (NIN == 2 && F0 == FV && F1 == FV) ? 5 : 
   if (p.csize > 1) {
     // cluster of csize CTAs (same column tile, consecutive row ranges): fold through distributed shared memory,
     // in rank order, on the rank-0 CTA -- csize times fewer partial rows, no second pass over them when nparts == 1
-    __shared__ float cs[128];
+    __shared__ float cs[TX * 4];
     if (ty == 0) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float a = sm[0][tx][j];
 #pragma unroll
-        for (int t = 1; t < 8; ++t) a = red_combine<RED>(a, sm[t][tx][j]);
+        for (int t = 1; t < TY; ++t) a = red_combine<RED>(a, sm[t][tx][j]);
         cs[tx * 4 + j] = a;                                   // columns past I hold the identity
       }
     }
     red_cluster_sync();
     const uint32_t crank = red_cluster_ctarank();
-    if (crank == 0 && threadIdx.x < 128) {
+    if (crank == 0 && threadIdx.x < TX * 4) {
       float a = cs[threadIdx.x];
       for (uint32_t r = 1; r < p.csize; ++r) a = red_combine<RED>(a, red_ld_dsmem(&cs[threadIdx.x], r));
-      const uint32_t c = blockIdx.x * 128 + threadIdx.x;
+      const uint32_t c = blockIdx.x * (TX * 4) + threadIdx.x;
       if (c < p.I) {
         if (p.to_partial) p.dst[((int64_t)o2 * p.nparts + split / p.csize) * p.I + c] = a;
         else final_store(p, p.dst + (int64_t)o2 * p.os2 + c, a);
@@ -408,7 +412,7 @@ __global__ void __launch_bounds__(256, (NIN == 2 && F0 == FV && F1 == FV) ? 5 : 
     for (int j = 0; j < 4; ++j) {
       float a = sm[0][tx][j];
 #pragma unroll
-      for (int t = 1; t < 8; ++t) a = red_combine<RED>(a, sm[t][tx][j]);
+      for (int t = 1; t < TY; ++t) a = red_combine<RED>(a, sm[t][tx][j]);
       if (p.to_partial) p.dst[((int64_t)o2 * p.nparts + split) * p.I + col + j] = a;
       else final_store(p, p.dst + (int64_t)o2 * p.os2 + col + j, a);
     }
@@ -427,7 +431,7 @@ __global__ void __launch_bounds__(256, (NIN == 2 && F0 == FV && F1 == FV) ? 5 : 
 #pragma unroll
   for (int j = 0; j < 4; ++j) t4[j] = red_identity<RED>();
   if (active) {
-    for (uint32_t k = ty; k < p.nparts; k += 8) {
+    for (uint32_t k = ty; k < p.nparts; k += TY) {
       const float4 v = __ldcg((const float4*)(p.dst + ((int64_t)o2 * p.nparts + k) * p.I + col));
       t4[0] = red_combine<RED>(t4[0], v.x); t4[1] = red_combine<RED>(t4[1], v.y);
       t4[2] = red_combine<RED>(t4[2], v.z); t4[3] = red_combine<RED>(t4[3], v.w);
@@ -441,7 +445,7 @@ __global__ void __launch_bounds__(256, (NIN == 2 && F0 == FV && F1 == FV) ? 5 : 
     for (int j = 0; j < 4; ++j) {
       float a = sm[0][tx][j];
 #pragma unroll
-      for (int t = 1; t < 8; ++t) a = red_combine<RED>(a, sm[t][tx][j]);
+      for (int t = 1; t < TY; ++t) a = red_combine<RED>(a, sm[t][tx][j]);
       final_store(p, p.final_dst + (int64_t)o2 * p.os2 + col + j, a);
     }
   }
@@ -643,22 +647,28 @@ static void launch_col_kernel(K kern, dim3 grid, const RedParams& p) {
   cfg.attrs = &attr; cfg.numAttrs = 1;
   cudaLaunchKernelEx(&cfg, kern, p);
 }
-template <int OP, int NIN, int RED>
-static bool launch_col_forms(const int (&f)[2], dim3 grid, const RedParams& p) {
+template <int OP, int NIN, int RED, int TX>
+static bool launch_col_forms_tx(const int (&f)[2], dim3 grid, const RedParams& p) {
   if constexpr (NIN == 1) {
-    launch_col_kernel(red_col_f32<OP, 1, RED, FV, FV>, grid, p);
+    launch_col_kernel(red_col_f32<OP, 1, RED, FV, FV, TX>, grid, p);
     return true;
   } else if constexpr (NIN == 2) {
-    if (f[0] == FV && f[1] == FV) launch_col_kernel(red_col_f32<OP, 2, RED, FV, FV>, grid, p);
-    else if (f[0] == FV && f[1] == FS) launch_col_kernel(red_col_f32<OP, 2, RED, FV, FS>, grid, p);
-    else if (f[0] == FS && f[1] == FV) launch_col_kernel(red_col_f32<OP, 2, RED, FS, FV>, grid, p);
-    else if (f[0] == FV && f[1] == FK) launch_col_kernel(red_col_f32<OP, 2, RED, FV, FK>, grid, p);
-    else if (f[0] == FK && f[1] == FV) launch_col_kernel(red_col_f32<OP, 2, RED, FK, FV>, grid, p);
+    if (f[0] == FV && f[1] == FV) launch_col_kernel(red_col_f32<OP, 2, RED, FV, FV, TX>, grid, p);
+    else if (f[0] == FV && f[1] == FS) launch_col_kernel(red_col_f32<OP, 2, RED, FV, FS, TX>, grid, p);
+    else if (f[0] == FS && f[1] == FV) launch_col_kernel(red_col_f32<OP, 2, RED, FS, FV, TX>, grid, p);
+    else if (f[0] == FV && f[1] == FK) launch_col_kernel(red_col_f32<OP, 2, RED, FV, FK, TX>, grid, p);
+    else if (f[0] == FK && f[1] == FV) launch_col_kernel(red_col_f32<OP, 2, RED, FK, FV, TX>, grid, p);
     else return false;
     return true;
   } else {
     return false;
   }
+}
+template <int OP, int NIN, int RED>
+static bool launch_col_forms(const int (&f)[2], dim3 grid, const RedParams& p, int tx) {
+  if (tx == 16) return launch_col_forms_tx<OP, NIN, RED, 16>(f, grid, p);
+  if (tx == 8) return launch_col_forms_tx<OP, NIN, RED, 8>(f, grid, p);
+  return launch_col_forms_tx<OP, NIN, RED, 32>(f, grid, p);
 }
 
 template <int OP, int NIN, int RED>
@@ -740,41 +750,35 @@ static int launch_fast_red(const RedPlan& pl, RedParams p, int vec, float* out, 
   // column pattern
   const int64_t R = pl.d1, I = pl.d0, O2 = pl.d2;
   p.L = (uint32_t)R; p.I = (uint32_t)I; p.os2 = pl.ostr[0];
-  const int tile = 32 * vec;
+  // f32 form kernels: ONE launch, ONE resident wave.  The 8 CTAs that share a column tile and own consecutive row
+  // ranges form a thread-block cluster along the split axis and fold their column sums through distributed shared
+  // memory (rank order: deterministic) -- no partial rows in global memory, no second pass, no tickets.  The tile is
+  // narrowed (128 / 64 / 32 columns, never less than one 128-B line per row) until >= 3 CTAs per SM exist.
+  // Measured on 2^26 elements (profiles/r02_microbench_elementwise.txt): two launches over 3.5 k short CTAs
+  // 50.3 us = 0.81 of the HBM peak; clusters over the same short CTAs 60 us (a cluster holds its slots until its
+  // slowest member is done, at each of 4 wave boundaries); one wave, 4 rows in flight per thread 47.7 us; 8 rows
+  // 46.0 us = 0.89; more than 8 splits (partial rows + tickets among the cluster leaders) 50-58 us.
+  // MDB_RED_COL_CLUSTER=0: the two-launch scheme (also used when the rows are too few to split 8 ways).
+  static const bool col_cluster = !(getenv("MDB_RED_COL_CLUSTER") && atoi(getenv("MDB_RED_COL_CLUSTER")) == 0);
+  int tx = 32;
+  uint32_t csize = 1;
+  if (col_cluster && vec == 4 && forms_ok && R >= 512) {
+    for (int t : {32, 16, 8}) {
+      tx = t;
+      if (((I + 4 * t - 1) / (4 * t)) * O2 * 8 >= (int64_t)g_sm_count * 3) break;
+    }
+    if (((I + 4 * tx - 1) / (4 * tx)) * O2 * 16 >= (int64_t)g_sm_count * 3) csize = 8;      // >= 1.5 CTAs per SM
+    else tx = 32;                                        // too few columns for one wave: split the rows further, two launches
+  }
+  const int tile = tx * vec;
   const int64_t gx = (I + tile - 1) / tile;
   int64_t want = ((int64_t)g_sm_count * 24 + gx * O2 - 1) / (gx * O2);   // ~4 full waves (8 CTAs/SM gave 1.37 waves: 27 % tail)
   int64_t maxsplit = std::max<int64_t>(1, R / 64);
   uint32_t nsplit = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(std::min(want, maxsplit), 1024));
   if ((int64_t)nsplit * I * O2 >= (int64_t(1) << 31)) nsplit = 1;
+  if (csize > 1) nsplit = csize;
   uint32_t seg = (uint32_t)((R + nsplit - 1) / nsplit);
-  nsplit = (uint32_t)((R + seg - 1) / seg);
-  // f32 form kernels with >= 8 splits: clusters of 4..8 CTAs along the split axis fold their column sums through
-  // distributed shared memory (fixed rank order), so only nsplit / csize partial rows reach global memory; the
-  // cluster leaders of a column tile take a ticket and the last one folds those rows -- ONE launch.  Measured on
-  // 2^26 elements (two launches: 50.3 us = 0.81 of the HBM peak): clusters over the SAME 3.5 k short CTAs 60 us (a
-  // cluster holds its slots until its slowest member is done, at every one of 4 wave boundaries); one resident
-  // wave of long CTAs 47.7-48.6 us = 0.85.  MDB_RED_COL_CLUSTER=0 two launches, 1 short CTAs, 2 (default) one wave.
-  static const int col_cluster = getenv("MDB_RED_COL_CLUSTER") ? atoi(getenv("MDB_RED_COL_CLUSTER")) : 2;
-  uint32_t csize = 1;
-  if (col_cluster && vec == 4 && forms_ok && nsplit >= 8 && gx * O2 <= kTickets) {
-    csize = 8;
-    if (col_cluster == 2) {
-      // ONE resident wave of long CTAs (clusters wait for their slowest member: short CTAs in several waves lose
-      // slots at every cluster boundary): the largest split count that fits the resident slots and has a
-      // cluster-sized divisor
-      const int64_t slots = (int64_t)g_sm_count * 6;
-      const int64_t nmax = std::min<int64_t>(std::max<int64_t>(8, slots / (gx * O2)), std::max<int64_t>(8, R / 64));
-      nsplit = 8;                                        // < 16 splits fit: 8 (one cluster per tile, no partial rows)
-      for (int64_t n = nmax; nmax >= 16 && n >= nmax - 7; --n) {
-        uint32_t c = 0;
-        for (uint32_t d = 8; d >= 4; --d) if (n % d == 0) { c = d; break; }
-        if (c) { nsplit = (uint32_t)n; csize = c; break; }
-      }
-    } else {
-      nsplit = (nsplit + 7) / 8 * 8;                     // trailing CTAs may own no rows: they contribute the identity
-    }
-    seg = (uint32_t)((R + nsplit - 1) / nsplit);
-  }
+  if (csize == 1) nsplit = (uint32_t)((R + seg - 1) / seg);
   const uint32_t nparts = nsplit / csize;
   p.seg = seg; p.nsplit = nsplit; p.csize = csize; p.nparts = nparts;
   TempBuf tmp;
@@ -786,16 +790,16 @@ static int launch_fast_red(const RedPlan& pl, RedParams p, int vec, float* out, 
   }
   dim3 grid((unsigned)gx, nsplit, (unsigned)O2);
   // Per-CTA tickets are NOT used for column sums: measured 52.8 vs 50.6 us on (8192,8192) -- the fence + ticket in
-  // each of the 3.5 k short CTAs costs more than the 5 us second launch it saves.  With clusters only the leaders
-  // (1 in 8) take one.  MDB_RED_COL_TICKETS=1 turns the per-CTA scheme on for measurements.
+  // each of the 3.5 k short CTAs costs more than the 5 us second launch it saves.  MDB_RED_COL_TICKETS=1 turns the
+  // scheme on for measurements.
   static const bool col_tickets = getenv("MDB_RED_COL_TICKETS") != nullptr;
-  if ((col_tickets || csize > 1) && vec == 4 && forms_ok && nparts > 1 && gx * O2 <= kTickets) {
+  if (col_tickets && vec == 4 && forms_ok && nparts > 1 && gx * O2 <= kTickets) {
     p.tickets = ticket_pool();
     p.final_dst = out;
   }
   bool used_forms = false;
   if (vec == 4) {
-    if (forms_ok && (used_forms = launch_col_forms<OP, NIN, RED>(form, grid, p))) {}
+    if (forms_ok && (used_forms = launch_col_forms<OP, NIN, RED>(form, grid, p, tx))) {}
     else if (csize > 1) return MDB_EINVAL;               // unreachable: classify_forms() admits only launchable forms
     else if (NIN > 1 && late) red_col<OP, NIN, RED, 4, (NIN > 1)><<<grid, 256, 0, g_stream>>>(p);
     else red_col<OP, NIN, RED, 4><<<grid, 256, 0, g_stream>>>(p);
