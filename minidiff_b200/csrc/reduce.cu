@@ -664,10 +664,17 @@ static bool launch_col_forms_tx(const int (&f)[2], dim3 grid, const RedParams& p
     return false;
   }
 }
+// the narrow tiles are only instantiated for the sums autodiff issues on big operands (plain sums, products,
+// the ReLU mask): every other fused form keeps 128-column tiles (compile time)
+template <int OP>
+constexpr bool kNarrowColTiles = (OP == MDB_OP_COPY || OP == MDB_OP_MUL || OP == MDB_OP_RELU_MASK_BWD);
+
 template <int OP, int NIN, int RED>
 static bool launch_col_forms(const int (&f)[2], dim3 grid, const RedParams& p, int tx) {
-  if (tx == 16) return launch_col_forms_tx<OP, NIN, RED, 16>(f, grid, p);
-  if (tx == 8) return launch_col_forms_tx<OP, NIN, RED, 8>(f, grid, p);
+  if constexpr (kNarrowColTiles<OP>) {
+    if (tx == 16) return launch_col_forms_tx<OP, NIN, RED, 16>(f, grid, p);
+    if (tx == 8) return launch_col_forms_tx<OP, NIN, RED, 8>(f, grid, p);
+  }
   return launch_col_forms_tx<OP, NIN, RED, 32>(f, grid, p);
 }
 
@@ -765,7 +772,7 @@ static int launch_fast_red(const RedPlan& pl, RedParams p, int vec, float* out, 
   if (col_cluster && vec == 4 && forms_ok && R >= 512) {
     for (int t : {32, 16, 8}) {
       tx = t;
-      if (((I + 4 * t - 1) / (4 * t)) * O2 * 8 >= (int64_t)g_sm_count * 3) break;
+      if (!kNarrowColTiles<OP> || ((I + 4 * t - 1) / (4 * t)) * O2 * 8 >= (int64_t)g_sm_count * 3) break;
     }
     if (((I + 4 * tx - 1) / (4 * tx)) * O2 * 16 >= (int64_t)g_sm_count * 3) csize = 8;      // >= 1.5 CTAs per SM
     else tx = 32;                                        // too few columns for one wave: split the rows further, two launches
