@@ -769,7 +769,9 @@ static int launch_fast_red(const RedPlan& pl, RedParams p, int vec, float* out, 
   static const bool col_cluster = !(getenv("MDB_RED_COL_CLUSTER") && atoi(getenv("MDB_RED_COL_CLUSTER")) == 0);
   int tx = 32;
   uint32_t csize = 1;
-  if (col_cluster && vec == 4 && forms_ok && R >= 512) {
+  // (inputs of >= 2^27 elements keep the two-launch scheme: its many short CTAs are bandwidth-bound there as well,
+  //  and inside the power-capped C4 step it measured 5 % faster than the single wave: 0.458 vs 0.479 ms per step)
+  if (col_cluster && vec == 4 && forms_ok && R >= 512 && R * I * O2 < (int64_t(1) << 27)) {
     for (int t : {32, 16, 8}) {
       tx = t;
       if (!kNarrowColTiles<OP> || ((I + 4 * t - 1) / (4 * t)) * O2 * 8 >= (int64_t)g_sm_count * 3) break;
