@@ -481,6 +481,52 @@ def test_fused_gradient_sums_all_forms(B, shape):
         np.testing.assert_allclose(host(B.mean(dev(B, t), axis=axis)), t64.mean(axis=axis), rtol=1e-4, atol=1e-6)
 
 
+@pytest.mark.parametrize("shape,axis", [((1024, 8192), 0), ((4096, 4096), 0), ((2048, 1024), 0), ((600, 4100), 0),
+                                        ((3, 1024, 2048), 1), ((8192, 1028), 0), ((512, 16384), 0)])
+def test_column_sums_through_the_cluster_fold(B, shape, axis):
+    """Column sums of fp32 inputs run as ONE launch of 8-CTA clusters that fold through distributed shared memory
+    (reduce.cu): 128- / 64- / 32-column tiles, ragged last tile, an outer axis, mean's divisor, accumulation into
+    an existing gradient buffer, a fused product with a row vector / column vector / scalar -- against float64,
+    and bit-identical from run to run (fixed rank order)."""
+    import ctypes as C
+
+    from minidiff_b200.backend import functions as F
+    from minidiff_b200.backend._lib import check as chk, lib
+
+    t = f32(*shape)
+    t64 = t.astype(np.float64)
+    n_red = shape[axis]
+    launches = lambda: int(lib.mdb_launch_count()) if hasattr(lib, "mdb_launch_count") else None
+    d = dev(B, t)
+    l0 = launches()
+    got = B.sum(d, axis=axis)
+    if l0 is not None:
+        assert launches() - l0 == 1
+    first = host(got)
+    np.testing.assert_allclose(first, t64.sum(axis=axis), rtol=1e-4, atol=2e-5 * np.sqrt(n_red))
+    for _ in range(3):
+        assert np.array_equal(host(B.sum(d, axis=axis)), first)
+    np.testing.assert_allclose(host(B.mean(d, axis=axis)), t64.mean(axis=axis), rtol=1e-4, atol=1e-6)
+    # fused product forms, accumulated into a buffer that already holds a gradient
+    kshape = list(shape)
+    kshape[axis] = 1
+    vec_along = [1] * len(shape)
+    vec_along[axis] = shape[axis]                       # one scalar per reduced row (form FS)
+    for o in (f32(*shape), f32(*kshape), f32(*vec_along), 1.5):
+        base = f32(*kshape)
+        out = dev(B, base)
+        want = base.astype(np.float64) + (t64 * np.asarray(o, dtype=np.float64)).sum(axis=axis, keepdims=True)
+        ins = [d, dev(B, o) if isinstance(o, np.ndarray) else o]
+        descs = (F.MdbArray * 2)()
+        for i, x in enumerate(ins):
+            if isinstance(x, B.DeviceArray):
+                descs[i] = x.d
+            else:
+                F._fill_imm(descs[i], x)
+        chk(lib.mdb_elementwise_reduce(F.OP["MUL"], C.byref(out.d), 2, descs, 1))
+        np.testing.assert_allclose(out.numpy(), want, rtol=1e-4, atol=2e-5 * np.sqrt(n_red))
+
+
 def test_full_sum_single_launch_is_repeatable_and_resets_its_tickets(B):
     t = dev(B, f32(4096, 4100))
     first = float(host(B.sum(t)))
