@@ -47,6 +47,10 @@
 // distinct operand panels; TMA loads and C stores can carry L2 eviction hints (off by default: measured
 // useless to harmful, profiles/r02_gemm_dram_traffic.md).
 // Fused epilogue (linear_relu): C = relu?( A@B + bias? ) * (mask_src > 0)?
+// Operand split (template kHybrid): false = 3xTF32, the default (converters write fp32 lo tiles, 12 MMAs per k-block);
+// true = the opt-in "fast" split (converters write K-major BF16 hb / lb tiles, 4 TF32 + 4 BF16 MMAs), see below.
+// Promotion: chains of p.chunk k-blocks in tensor memory, then sum = fma(chain, 1 + rz_gain * n, sum) in registers
+// (compensates the accumulator's round-toward-zero bias; exact chain sums are passed through unchanged).
 constexpr int kPairThreads = 512;
 constexpr int kPairConvWarps = 4, kPairEpiWarps = 8;
 constexpr int PBN = 128;          // B rows staged per CTA; the UMMA N is 2 * PBN

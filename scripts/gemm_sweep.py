@@ -1,5 +1,6 @@
-"""A/B timing of the CTA-pair GEMM planner knobs (tile order, L2 hints, stream-K) on the GEMM shapes of
-the C4 step (per-GPU batch B) and C3.     python scripts/gemm_sweep.py [B] [rounds] [shape,shape..]
+"""A/B timing of the CTA-pair GEMM planner knobs (tile order, L2 hints, stream-K; SWEEP=flags: kernel flags;
+SWEEP=split: operand split x chain length) on the GEMM shapes of the C4 step (per-GPU batch B) and C3.
+    python scripts/gemm_sweep.py [B] [rounds] [shape,shape..]
 All variants of a shape are timed INTERLEAVED (round-robin, several rounds, after a warm-up that
 brings the chip to its power-capped steady state), so they see the same clocks: a sequential sweep
 gave the first variant 10-15 % for free.  Prints the median ms and TFLOP/s (2MNK) per variant."""
