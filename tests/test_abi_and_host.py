@@ -54,6 +54,17 @@ def test_backend_table_has_the_114_reference_names():
 
 
 @pytest.mark.skipif(_lib.device_available(), reason="only meaningful without a GPU")
+def test_matmul_split_switch_is_host_only_state():
+    """backend.set_matmul_split: the two operand splits of the tensor-core GEMM by name, anything else a ValueError
+    (no device needed: the knob is host state of the library)."""
+    B.set_matmul_split("fast")
+    B.set_matmul_split("3xtf32")
+    with pytest.raises(ValueError):
+        B.set_matmul_split("tf32")
+    for knob in (8, 9, 10):                      # SPLIT, CHUNK, RZ_GAIN back to their defaults
+        _lib.check(_lib.lib.mdb_gemm_knob(knob, -1))
+
+
 def test_no_cpu_fallback_without_a_device():
     with pytest.raises(RuntimeError, match="no CPU path"):
         B.ones((2, 2))
