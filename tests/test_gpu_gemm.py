@@ -377,16 +377,26 @@ def test_fused_epilogue_is_bit_identical_to_the_unfused_chain(B, knobs, M, K, N,
     assert F._gemm_fused(small[2], small[3], relu=True) is None
 
 
-def test_pair_kernel_soak_is_bitwise_repeatable(B, knobs):
+@pytest.mark.parametrize("split", ["3xtf32", "fast"])
+def test_pair_kernel_soak_is_bitwise_repeatable(B, knobs, split):
     """Soak of the cross-CTA hand-offs (plain mbarrier.arrive.shared::cluster from the peer CTA, stream-K
-    flags through global memory): many back-to-back launches of the BASELINE shapes, the output hash
-    must be identical every time (a race in the hand-off would show as a changed bit)."""
+    flags through global memory) and of the converters' shared-memory tiles, for both operand splits: many
+    back-to-back launches of the BASELINE shapes, the output hash must be identical every time (a race in a
+    hand-off would show as a changed bit)."""
     import zlib
 
     from minidiff_b200.backend import functions as F
 
     knobs(streamk=-1)
-    for (M, K, N), reps in (((8192, 8192, 8192), 200), ((4096, 65536, 1024), 300), ((4096, 16384, 4096), 300)):
+    B.set_matmul_split(split)
+    try:
+        _soak(B, F, zlib, (200, 300, 300) if split == "3xtf32" else (100, 150, 150))
+    finally:
+        B.set_matmul_split("3xtf32")
+
+
+def _soak(B, F, zlib, all_reps):
+    for ((M, K, N), reps) in zip(((8192, 8192, 8192), (4096, 65536, 1024), (4096, 16384, 4096)), all_reps):
         rng = np.random.default_rng(M + N)
         da = B.asarray(rng.standard_normal((M, K), dtype=np.float32))
         db = B.asarray(rng.standard_normal((K, N), dtype=np.float32))
